@@ -148,8 +148,8 @@ def test_noise():
         w, b = oracle.noisy(g[name + "_x_in"], g[name + "_x_out"])
         # torch-CPU's sqrt_ goes through MKL VML (vsSqrt), which is 1 ulp off the correctly rounded
         # value for ~0.7% of inputs [probe]; the oracle (and the CUDA kernel) use IEEE sqrtf.  So the
-        # contract here is 1 ulp per factor -> 2 ulp on the product, not bit equality.
-        np.testing.assert_allclose(w, g[name + "_w_eps"], rtol=2.5e-7, atol=0)
+        # contract here is 1 ulp per factor -> up to ~3 ulp on the rounded product, not bit equality.
+        np.testing.assert_allclose(w, g[name + "_w_eps"], rtol=4e-7, atol=0)
         np.testing.assert_allclose(b, g[name + "_b_eps"], rtol=1.3e-7, atol=0)
         frac_exact = np.mean(w.view(np.uint32) == g[name + "_w_eps"].view(np.uint32))
         assert frac_exact > 0.95
