@@ -1,0 +1,159 @@
+/*
+ * rainbow_b200.h -- C ABI of the B200-native Rainbow learner hot path.
+ *
+ * The reference (Kaixhin/Rainbow @ 1745b184) has no FFI/plugin layer: its hot
+ * path is Python (memory.py, agent.py, model.py).  This header is the drop-in
+ * boundary a maintainer of the reference would bind with ctypes/cffi from
+ * those three files (INTEGRATION.md shows the stubs).  Each entry point names
+ * the reference lines it replaces.
+ *
+ * Conventions
+ *   - C linkage, plain pointers and sizes, no torch / C++ types.
+ *   - Every pointer is a DEVICE pointer owned by the caller (e.g.
+ *     tensor.data_ptr()) unless a parameter is documented "host".
+ *   - Every call enqueues work on `stream` (a cudaStream_t passed as void*)
+ *     and returns immediately; nothing synchronises, allocates or frees.
+ *     All calls are CUDA-graph capturable.
+ *   - Return value: RB_OK (0) or a negative errno-style code; the text of the
+ *     last error of the calling thread is available from rb_last_error().
+ *   - Device-side conditions (rejected sample batch, bad index) are reported
+ *     through the `status` words written by the kernel, never by a sync.
+ *
+ * Data layout in HBM (structure of arrays; reference Transition_dtype is an
+ * array of 7069-byte structs, memory.py:7):
+ *   tree         float32[tree_start + size]   heap order, root at tree[0],
+ *                children 2i+1 / 2i+2, leaves from tree_start = 2^ceil(log2 size)-1
+ *                (memory.py:17-18).  For 128-byte-aligned level loads allocate
+ *                one pad float in front so that (tree - 1) is 128 B aligned.
+ *   frames       uint8[size][7056]            last frame of each transition
+ *   timestep     int32[size]                  in-episode step (0 = episode start)
+ *   action       int32[size]
+ *   reward       float32[size]
+ *   nonterminal  uint8[size]
+ *   ring_state   int64[4]  {head (next write slot), full (0/1), t_episode, appended_total}
+ *   running_max  float32[1] largest exponentiated priority seen (memory.py:20,48)
+ *   rng_counter  uint64[1]  Philox draw counter, advanced by the kernels themselves
+ *                           (so a replayed CUDA graph draws fresh numbers)
+ */
+#ifndef RAINBOW_B200_H
+#define RAINBOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_ABI_VERSION 1
+
+#define RB_OK 0
+#define RB_ERR_INVAL (-22)       /* bad argument (EINVAL) */
+#define RB_ERR_RANGE (-34)       /* size outside supported range (ERANGE) */
+#define RB_ERR_CUDA (-5)         /* CUDA runtime reported an error (EIO) */
+
+#define RB_FRAME_BYTES 7056      /* 84*84 */
+#define RB_MAX_WINDOW 64         /* history + multi_step */
+#define RB_MAX_ATOMS 128
+#define RB_MAX_NOISY_LAYERS 8
+
+/* status word layout written by rb_tree_sample: status[0] = 1 if the batch now in the
+ * output buffers passed the whole-batch validity test, 0 otherwise; status[1] = draws used. */
+
+typedef void* rb_stream_t; /* cudaStream_t */
+
+int rb_abi_version(void);
+const char* rb_last_error(void);
+
+/* memory.py:157-159 ReplayMemory.update_priorities -> :44-48 SegmentTree.update
+ * (-> :28-33 _propagate -> :23-25 _update_nodes).
+ * leaf[tree_idx[k]] = raw_priority[k]^omega (duplicates: last k wins), parents recomputed
+ * level by level as fl32(left+right) up to the root, running_max = max(running_max, max_k leaf).
+ * omega_is_applied != 0 means raw_priority already holds exponentiated values (SegmentTree.update).
+ * status[0] is set to 1 if any tree_idx lies outside the leaf range (nothing is written for it). */
+int rb_tree_update(float* tree, int64_t tree_start, int64_t size, const int64_t* tree_idx,
+                   const float* raw_priority, float omega, int omega_is_applied, int B, float* running_max,
+                   int32_t* status, rb_stream_t stream);
+
+/* memory.py:79-82 SegmentTree.find (-> :64-76 _retrieve): float64 residual against float32 nodes,
+ * strict '>' goes right, child indices clipped to the last element on the leaf level. */
+int rb_tree_find(const float* tree, int64_t tree_start, int64_t size, const double* values, int B, float* probs,
+                 int64_t* data_idx, int64_t* tree_idx, rb_stream_t stream);
+
+/* memory.py:148-154 ReplayMemory.sample head + :124-132 _get_samples_from_segments:
+ * p_total = tree[0]; seg = fl32(p_total/B); v_k = seg*u_k + k*seg (float64); find; whole-batch
+ * validity test (memory.py:131) with redraw; importance weights (count*p/p_total)^-beta / max.
+ *   u01 != NULL : parity mode.  u01 is float64[u01_attempts][B] of unit uniforms (what
+ *                 RandomState.uniform consumes); attempt a uses row a; at most u01_attempts tries.
+ *   u01 == NULL : device Philox4x32-10 keyed by `seed`, counter *rng_counter (advanced by the
+ *                 number of draws); at most max_attempts tries.
+ * beta_dev (optional, may be NULL) overrides `beta` with a device scalar (graph replay). */
+int rb_tree_sample(const float* tree, int64_t tree_start, int64_t size, const int64_t* ring_state, int n,
+                   int history, const double* u01, int u01_attempts, uint64_t seed, uint64_t* rng_counter, int B,
+                   float beta, const float* beta_dev, int max_attempts, float* probs, int64_t* data_idx,
+                   int64_t* tree_idx, float* weights, int32_t* status, rb_stream_t stream);
+
+/* memory.py:111-121 _get_transitions + :134-145 (tail of _get_samples_from_segments) + :85-86 get:
+ * window of history+n records around each data_idx (indices mod size), episode-boundary blanking,
+ * states = u8/255 [B,history,84,84], next_states (window shifted by n), actions int64[B],
+ * returns = sum_k gamma_pow[k]*reward[B], nonterminals float32[B] (of the last window record). */
+int rb_gather(const uint8_t* frames, const int32_t* timestep, const int32_t* action, const float* reward,
+              const uint8_t* nonterminal, int64_t size, const int64_t* data_idx, int B, int history, int n,
+              const float* gamma_pow, float* states, float* next_states, int64_t* actions, float* returns,
+              float* nonterminals, rb_stream_t stream);
+
+/* memory.py:166-178 ReplayMemory.__next__, batched: states for current_idx = first .. first+count-1,
+ * backward-only blanking, negative indices wrap.  out is float32[count][history][84*84]. */
+int rb_iter_states(const uint8_t* frames, const int32_t* timestep, int64_t size, int64_t first, int count,
+                   int history, float* out, rb_stream_t stream);
+
+/* memory.py:105-108 ReplayMemory.append -> :56-61 SegmentTree.append (-> :51-54, :36-41):
+ * quantise the newest frame (f32*255, truncating cast), store the record at ring_state.head with
+ * timestep = ring_state.t_episode, set its leaf to *running_max and walk to the root, advance the
+ * head, set full on wrap, t_episode = terminal ? 0 : t_episode+1.
+ * state_last_frame: float32[84*84] device pointer (state[-1]). */
+int rb_append(float* tree, int64_t tree_start, int64_t size, uint8_t* frames, int32_t* timestep, int32_t* action,
+              float* reward, uint8_t* nonterminal, int64_t* ring_state, float* running_max,
+              const float* state_last_frame, int32_t action_value, float reward_value, int terminal,
+              rb_stream_t stream);
+
+/* agent.py:66-96 Agent.learn minus the three network bodies, given PRE-softmax logits [B,A,Z]
+ * (model.py:75 `q`; the softmax / log_softmax of model.py:76-79 are folded in):
+ * double-DQN argmax with the online net, target distribution, Tz clamp, l/u projection with the
+ * reference's fix-ups and accumulation order, loss_i = -sum m*logp (the TD priority of
+ * agent.py:100), and d(mean_i w_i*loss_i)/dq_online_s.  m_out / astar_out may be NULL. */
+int rb_c51_loss_grad(const float* q_online_s, const float* q_online_ns, const float* q_target_ns,
+                     const int64_t* actions, const float* returns, const float* nonterminals,
+                     const float* weights, const float* support, float vmin, float vmax, float delta_z,
+                     float gamma_n, int B, int A, int Z, float* loss, float* grad_q_online_s, float* m_out,
+                     int64_t* astar_out, rb_stream_t stream);
+
+/* model.py:82-85 DQN.reset_noise -> :36-40 NoisyLinear.reset_noise -> :32-34 _scale_noise, all
+ * layers of one net in one launch.  HOST arrays (length n_layers): weight_eps[l] -> float32[out][in],
+ * bias_eps[l] -> float32[out], in_features, out_features.
+ *   x_in / x_out != NULL : parity mode, raw standard normals, concatenated over layers in layer
+ *                          order (eps_in of layer 0, of layer 1, ... / eps_out likewise).
+ *   NULL                 : device Philox + Box-Muller keyed by seed and *rng_counter (+1 per call). */
+int rb_noisy_resample(float* const* weight_eps, float* const* bias_eps, const int* in_features,
+                      const int* out_features, int n_layers, const float* x_in, const float* x_out, uint64_t seed,
+                      uint64_t* rng_counter, rb_stream_t stream);
+
+/* model.py:43-44 NoisyLinear.forward weight composition W = mu + sigma*eps (elementwise),
+ * used for both weights ([out*in]) and biases ([out]). */
+int rb_noisy_compose(const float* mu, const float* sigma, const float* eps, int64_t count, float* out,
+                     rb_stream_t stream);
+
+/* agent.py:97-98 clip_grad_norm_(params, max_norm) + Adam.step() on FLAT float32 buffers of P
+ * elements (all online-net parameters laid out back to back).  `step_count` is a device int64 holding
+ * the number of steps already taken; the kernel increments it.  grad_scale multiplies the gradient
+ * before everything else (1/world_size after a SUM all-reduce; 1.0 on one GPU).
+ * partial_sums: scratch float64[rb_clip_adam_scratch_elems()].  norm_out (optional) receives the
+ * pre-clip global L2 norm. */
+int rb_clip_adam_scratch_elems(void);
+int rb_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t P, float grad_scale,
+                 float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_count,
+                 double* partial_sums, float* norm_out, rb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAINBOW_B200_H */

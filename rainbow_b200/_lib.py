@@ -1,0 +1,79 @@
+"""ctypes binding of include/rainbow_b200.h.
+
+The product path has NO CPU fallback: if librainbow_b200.so is missing and cannot be built, or a
+kernel is asked to run on a non-CUDA tensor, this module raises.
+"""
+import ctypes as C
+import os
+
+from . import _build
+
+_lib = None
+
+_vp, _i64, _i32, _f32, _u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64
+
+# name -> (restype, argtypes); must list every symbol declared in include/rainbow_b200.h
+SIGNATURES = {
+    "rb_abi_version": (C.c_int, []),
+    "rb_last_error": (C.c_char_p, []),
+    "rb_tree_update": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _f32, _i32, _i32, _vp, _vp, _vp]),
+    "rb_tree_find": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "rb_tree_sample": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _i32, _vp, _i32, _u64, _vp, _i32, _f32, _vp, _i32,
+                                 _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rb_gather": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rb_iter_states": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
+    "rb_append": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, _f32, _i32, _vp]),
+    "rb_c51_loss_grad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32, _i32, _i32,
+                                   _vp, _vp, _vp, _vp, _vp]),
+    "rb_noisy_resample": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _u64, _vp, _vp]),
+    "rb_noisy_compose": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "rb_clip_adam_scratch_elems": (C.c_int, []),
+    "rb_clip_adam": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
+}
+
+
+class RainbowB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load (building first if the .so is absent or older than its source) and type the C ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _build.stale():
+        try:
+            _build.build()
+        except Exception as e:  # no silent fallback
+            if not os.path.exists(_build.SO):
+                raise RainbowB200Error(f"librainbow_b200.so is missing and could not be built: {e}") from e
+    lib = C.CDLL(_build.SO)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.rb_abi_version() != 1:
+        raise RainbowB200Error("librainbow_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RainbowB200Error(f"rainbow_b200 C ABI error {rc}: {load().rb_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a CUDA tensor (None -> NULL).  Refuses host tensors: there is no CPU path."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RainbowB200Error("rainbow_b200 kernels need CUDA tensors (no CPU fallback exists)")
+    if not t.is_contiguous():
+        raise RainbowB200Error("rainbow_b200 kernels need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,241 @@
+"""Rainbow learner: the reference's Agent API (agent.py:12-118) over B200-native kernels.
+
+One `learn(mem)` (agent.py:61-100) is:
+
+    K1 rb_tree_sample + K2 rb_gather          (mem.sample, memory.py:148-155)
+    3 x DQN.logits (torch: cuDNN / cuBLAS)    (agent.py:66,71,75)
+    K6 rb_noisy_resample (target net)         (agent.py:74)
+    K3 rb_c51_loss_grad                       (agent.py:67,72-73,76-96 + softmax halves of model.py:76-79)
+    torch autograd backward from d loss / d logits
+    [NCCL all-reduce of the flat gradient when world_size > 1]
+    K7 rb_clip_adam                           (agent.py:97-98)
+    K4 rb_tree_update                         (agent.py:100 -> memory.py:157-159)
+
+Nothing in that chain synchronises with the host, so the whole update is captured into one CUDA graph
+(`cuda_graph=True`, the default) and replayed: the update is launch-latency bound otherwise
+(the reference issues ~600 ATen ops per update).
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from .dist import GradSync
+from .memory import ReplayMemory, _SampleWorkspace
+from .model import DQN
+
+
+def c51_loss_grad(q_online_s, q_online_ns, q_target_ns, actions, returns, nonterminals, weights, support, vmin, vmax,
+                  delta_z, gamma_n, loss=None, grad=None, m_out=None, astar_out=None):
+    """Launch K3 on pre-softmax logits [B,A,Z]; returns (loss[B], grad[B,A,Z])."""
+    B, A, Z = q_online_s.shape
+    dev = q_online_s.device
+    if loss is None:
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+    if grad is None:
+        grad = torch.empty((B, A, Z), dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().rb_c51_loss_grad(
+        _lib.ptr(q_online_s), _lib.ptr(q_online_ns), _lib.ptr(q_target_ns), _lib.ptr(actions), _lib.ptr(returns),
+        _lib.ptr(nonterminals), _lib.ptr(weights), _lib.ptr(support), float(vmin), float(vmax), float(delta_z),
+        float(gamma_n), B, A, Z, _lib.ptr(loss), _lib.ptr(grad), _lib.ptr(m_out), _lib.ptr(astar_out), _lib.stream()))
+    return loss, grad
+
+
+class FusedClipAdam:
+    """clip_grad_norm_ + Adam (agent.py:46,97-98) over ONE flat parameter buffer.
+
+    The network's parameters are re-pointed at slices of `flat_param` (each slice starts on a 256-byte
+    boundary; padding stays zero), their .grad at slices of `flat_grad`, so the optimiser step is two kernel
+    launches (sum of squares, then clip+Adam) and the multi-GPU gradient exchange is a single all-reduce."""
+
+    ALIGN = 64  # elements
+
+    def __init__(self, net, lr, eps, max_norm, betas=(0.9, 0.999)):
+        self.params = [p for p in net.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += -(-p.numel() // self.ALIGN) * self.ALIGN
+        self.numel = off
+        self.lr, self.eps, self.max_norm, self.betas = float(lr), float(eps), float(max_norm), betas
+        self.flat_param = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._lib = _lib.load()
+        self._partial = torch.zeros(self._lib.rb_clip_adam_scratch_elems(), dtype=torch.float64, device=dev)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                n = p.numel()
+                self.flat_param[o:o + n].copy_(p.reshape(-1))
+                p.data = self.flat_param[o:o + n].view_as(p)
+                p.grad = self.flat_grad[o:o + n].view_as(p)
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def step(self, grad_scale=1.0):
+        _lib.check(self._lib.rb_clip_adam(
+            _lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+            self.numel, float(grad_scale), self.max_norm, self.lr, self.betas[0], self.betas[1], self.eps,
+            _lib.ptr(self.step_count), _lib.ptr(self._partial), _lib.ptr(self.grad_norm), _lib.stream()))
+
+    def state_dict(self):
+        return dict(step=int(self.step_count.item()), exp_avg=self.exp_avg.clone(), exp_avg_sq=self.exp_avg_sq.clone(),
+                    lr=self.lr, eps=self.eps, betas=self.betas, max_norm=self.max_norm)
+
+    def load_state_dict(self, sd):
+        self.step_count.fill_(int(sd["step"]))
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+
+
+class Agent:
+    def __init__(self, args, env):
+        self.device = torch.device(args.device)
+        if self.device.type != "cuda":
+            raise _lib.RainbowB200Error(f"rainbow_b200.Agent needs a CUDA device, got '{self.device}' (no CPU fallback)")
+        self.action_space = env.action_space()
+        self.atoms = args.atoms
+        self.Vmin = args.V_min
+        self.Vmax = args.V_max
+        self.support = torch.linspace(args.V_min, args.V_max, self.atoms).to(device=self.device)  # agent.py:18
+        self.delta_z = (args.V_max - args.V_min) / (self.atoms - 1)
+        self.batch_size = args.batch_size
+        self.n = args.multi_step
+        self.discount = args.discount
+        self.norm_clip = args.norm_clip
+
+        self.online_net = DQN(args, self.action_space).to(device=self.device)
+        model_path = getattr(args, "model", None)
+        if model_path:  # agent.py:26-36: pretrained weights, with the old conv key names re-mapped
+            if not os.path.isfile(model_path):
+                raise FileNotFoundError(model_path)
+            state_dict = torch.load(model_path, map_location="cpu")
+            for i, old in enumerate(("conv1", "conv2", "conv3")):
+                for kind in ("weight", "bias"):
+                    if f"{old}.{kind}" in state_dict:
+                        state_dict[f"convs.{2 * i}.{kind}"] = state_dict.pop(f"{old}.{kind}")
+            self.online_net.load_state_dict(state_dict)
+            print("Loading pretrained model: " + model_path)
+        self.online_net.train()
+
+        self.target_net = DQN(args, self.action_space).to(device=self.device)
+        self.sync = GradSync()  # no-op unless torch.distributed is initialised with world_size > 1
+        # distinct noise streams per net and per rank
+        self.online_net.noise_seed = (self.online_net.noise_seed * 2 + 1 + 7919 * self.sync.rank) & (2 ** 63 - 1)
+        self.target_net.noise_seed = (self.target_net.noise_seed * 2 + 2 + 7919 * self.sync.rank) & (2 ** 63 - 1)
+
+        self.optimiser = FusedClipAdam(self.online_net, lr=args.learning_rate, eps=args.adam_eps, max_norm=self.norm_clip)
+        self.sync.broadcast_(self.optimiser.flat_param)  # identical initial parameters on every rank
+        self.update_target_net()
+        self.target_net.train()
+        for p in self.target_net.parameters():
+            p.requires_grad = False
+
+        self.use_cuda_graph = bool(getattr(args, "cuda_graph", True))
+        self._graph = None
+        self._graph_key = None
+        self._ws = None
+        self._learn_calls = 0
+        self.last_loss = None  # per-sample losses of the most recent update (device tensor)
+
+    # ---- acting / evaluation (agent.py:49-59,110-118) ---------------------------------------------
+    def reset_noise(self):
+        self.online_net.reset_noise()
+
+    def act(self, state):
+        with torch.no_grad():
+            return (self.online_net(state.unsqueeze(0)) * self.support).sum(2).argmax(1).item()
+
+    def act_e_greedy(self, state, epsilon=0.001):
+        return np.random.randint(0, self.action_space) if np.random.random() < epsilon else self.act(state)
+
+    def evaluate_q(self, state):
+        with torch.no_grad():
+            return (self.online_net(state.unsqueeze(0)) * self.support).sum(2).max(1)[0].item()
+
+    def train(self):
+        self.online_net.train()
+
+    def eval(self):
+        self.online_net.eval()
+
+    def update_target_net(self):
+        self.target_net.load_state_dict(self.online_net.state_dict())
+
+    def save(self, path, name="model.pth"):
+        torch.save(self.online_net.state_dict(), os.path.join(path, name))
+
+    # ---- the update ------------------------------------------------------------------------------
+    def _update_from_batch(self, batch, target_noise=None):
+        """agent.py:66-98 on an already sampled batch; returns per-sample losses (device)."""
+        idxs, states, actions, returns, next_states, nonterminals, weights = batch
+        q_s = self.online_net.logits(states)
+        with torch.no_grad():
+            q_ns = self.online_net.logits(next_states)
+            if target_noise is None:
+                self.target_net.reset_noise()
+            else:
+                self.target_net.reset_noise(*target_noise)
+            q_t = self.target_net.logits(next_states)
+            loss, grad = c51_loss_grad(q_s.detach(), q_ns, q_t, actions, returns, nonterminals, weights, self.support,
+                                       self.Vmin, self.Vmax, self.delta_z, self.discount ** self.n)
+        self.optimiser.zero_grad()
+        q_s.backward(grad)
+        self.sync.all_reduce_(self.optimiser.flat_grad)
+        self.optimiser.step(grad_scale=1.0 / self.sync.world_size)
+        return loss
+
+    def _learn_eager(self, mem):
+        batch = mem.sample(self.batch_size)
+        loss = self._update_from_batch(batch)
+        if isinstance(mem, ReplayMemory):
+            mem.update_priorities(batch[0], loss)
+        else:  # a foreign (reference-style, host) memory: agent.py:100
+            mem.update_priorities(batch[0], loss.detach().cpu().numpy())
+        return loss
+
+    def _capture(self, mem):
+        """Record one whole update (sample -> ... -> priority write-back) into a CUDA graph.  Capturing does
+        not execute; the caller replays."""
+        ws = _SampleWorkspace(self.batch_size, mem.history, self.device)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            batch = mem.sample_into(ws)
+            loss = self._update_from_batch(batch)
+            mem.update_priorities(batch[0], loss)
+        self._graph, self._ws, self.last_loss = graph, ws, loss
+
+    GRAPH_WARMUP = 2  # eager updates before capture (cuDNN/cuBLAS plan selection, autograd buffers)
+
+    def learn(self, mem):
+        """agent.py:61-100.  Exactly one update per call: the first GRAPH_WARMUP calls run eagerly on a side
+        stream (torch's documented warm-up recipe for whole-step capture), the next call captures the graph and
+        every call from then on is one graph launch."""
+        graphable = (self.use_cuda_graph and isinstance(mem, ReplayMemory) and mem.rng == "philox")
+        key = (id(mem), self.batch_size)
+        if graphable and self._graph_key != key:
+            self._graph, self._graph_key, self._warm = None, key, 0
+        if not graphable:
+            self.last_loss = self._learn_eager(mem)
+        elif self._graph is None and self._warm < self.GRAPH_WARMUP:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self.last_loss = self._learn_eager(mem)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self._warm += 1
+        else:
+            if self._graph is None:
+                self._capture(mem)
+            mem.push_beta()
+            self._graph.replay()
+        self._learn_calls += 1
+        if self._learn_calls % 4096 == 0 and isinstance(mem, ReplayMemory):
+            mem.check_last_sample()
