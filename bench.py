@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- learner updates/sec of the Rainbow hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C3|C4]
+
+One step = `dqn.reset_noise(); dqn.learn(mem)` (reference main.py:150-151,163-164) on synthetic 84x84x4
+transitions.  N=1 workload = BASELINE.json configs[1] ("C2": 1M-transition replay in HBM, batch 32, 51
+atoms, n=3, canonical net).  N>1 (torchrun, one rank per GPU): every rank owns a private replay + stream
+and the ranks exchange only the flat gradient (NCCL all-reduce) -> weak scaling, value = per-rank batch-32
+updates summed over ranks per second.
+
+Printed JSON (one line, rank 0): value (inputs resident in HBM, CUDA-graph replay), e2e (through the public
+Agent/ReplayMemory API with HOST frames: 4 appends from pinned memory + update + loss read-back per step,
+like main.py's replay_frequency=4 loop), roofline of the dominant hand-written kernel (CUDA events around
+the kernel, live), cpu_baseline (oracle port of the reference's CPU path on this box's cores).
+
+--impl reference: the CPU arm (oracle/learner.py port of the reference path, all host threads), same
+metric/config/unit; under torchrun only rank 0 runs it.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: capacity, batch, n, architecture, hidden   
+    "C2": dict(cap=1_000_000, B=32, n=3, arch="canonical", hidden=512),
+    "C3": dict(cap=100_000, B=32, n=20, arch="data-efficient", hidden=256),
+    "C4": dict(cap=1_000_000, B=512, n=3, arch="canonical", hidden=512),
+}
+ACTIONS = 6
+REPLAY_FREQUENCY = 4  # main.py:37 -- env steps (appends) per learner update in the e2e loop
+
+
+def make_args(cfg, device):
+    return argparse.Namespace(device=device, history_length=4, discount=0.99, multi_step=cfg["n"], priority_weight=0.4,
+                              priority_exponent=0.5, atoms=51, V_min=-10.0, V_max=10.0, batch_size=cfg["B"],
+                              norm_clip=10.0, model=None, learning_rate=6.25e-5, adam_eps=1.5e-4,
+                              architecture=cfg["arch"], hidden_size=cfg["hidden"], noisy_std=0.1, cuda_graph=True)
+
+
+class FakeEnv:
+    def action_space(self):
+        return ACTIONS
+
+
+def synthetic_meta(cap, seed):
+    """BASELINE.md synthetic fill (everything except the frames), identical for both arms."""
+    rs = np.random.RandomState(seed)
+    timestep = (np.arange(cap) % 1000).astype(np.int32)
+    return dict(timestep=timestep, nonterminal=(timestep != 999).astype(np.uint8),
+                action=rs.randint(0, ACTIONS, cap).astype(np.int32), reward=rs.randint(-1, 2, cap).astype(np.float32),
+                priority=(rs.uniform(0, 1, cap) ** 0.5 + 1e-3).astype(np.float32), head=12345 % cap)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed regions run."""
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.max_mhz, self.ok = index, period, [], set(), None, False
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_cpu_port(cfg, updates, warmup, with_appends, seed=1):
+    """The reference's CPU path (oracle port) on this box's cores: returns updates/s over `updates` updates."""
+    import torch
+
+    from oracle.learner import OracleLearner, OracleReplay
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    np.random.seed(123)
+    cap = cfg["cap"]
+    args = make_args(cfg, "cpu")
+    mem = OracleReplay(cap, 4, cfg["n"], 0.99, 0.4, 0.5)
+    meta = synthetic_meta(cap, seed)
+    t = mem.tree
+    t.timestep[:], t.nonterminal[:], t.action[:], t.reward[:] = meta["timestep"], meta["nonterminal"], meta["action"], meta["reward"]
+    # frame bytes do not affect timing; a cheap non-constant fill touches every page of the 7 GB ring
+    pat = np.random.RandomState(seed).randint(0, 256, (1024, 7056), dtype=np.uint8)
+    for s in range(0, cap, 1024):
+        e = min(cap, s + 1024)
+        t.frames[s:e] = pat[:e - s]
+    for s in range(0, cap, 4096):
+        e = min(cap, s + 4096)
+        t.update(np.arange(s, e) + t.tree_start, meta["priority"][s:e])
+    t.index, t.full = meta["head"], True
+    learner = OracleLearner(args, ACTIONS)
+    frame_src = [torch.rand(4, 84, 84) for _ in range(8)]
+
+    def step(i):
+        if with_appends:
+            for j in range(REPLAY_FREQUENCY):
+                mem.append(frame_src[(i + j) % 8].numpy(), (i + j) % ACTIONS, float((i % 3) - 1), (i * 4 + j) % 1000 == 999)
+        learner.reset_noise()
+        learner.learn(mem)
+
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(updates):
+        step(warmup + i)
+    dt = time.perf_counter() - t0
+    return updates / dt, dt, torch.get_num_threads()
+
+
+def reference_arm(opts, cfg, rank):
+    """--impl reference: CPU arm.  The reference is pure Python and /root/reference does not exist on the GPU
+    box, so this times the oracle port (oracle/learner.py + oracle/rb_oracle.c), kind = "port"."""
+    if rank != 0:
+        return
+    per_step = 1  # one update (preceded by its 4 appends) per bench "step", exactly like our arm's e2e step
+    ups, dt, threads = run_cpu_port(cfg, opts.steps * per_step, max(3, opts.warmup), with_appends=True)
+    total = opts.steps * per_step
+    line = {"impl": "reference", "metric": "learner updates/sec (batch32, 1M buffer, 51 atoms)", "value": ups,
+            "unit": "updates/s", "n_gpus": opts.gpus, "steps": opts.steps, "warmup": opts.warmup,
+            "ms_per_step": 1e3 * dt / opts.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "gpu_launches": 0,
+            "config": workload_config(opts.config, cfg, opts.gpus),
+            "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": threads, "kind": "port",
+                             "sample": f"{total} updates ({per_step} per bench step), each preceded by {REPLAY_FREQUENCY} appends, "
+                                       f"after {max(3, opts.warmup)} warm-up updates; replay tree/gather in C (oracle), nets in torch-CPU "
+                                       f"with {threads} threads"},
+            "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, cfg, gpus):
+    return {"workload": f"{name}: synthetic 84x84x4 transitions, {cfg['cap']}-transition replay per GPU, batch {cfg['B']} per GPU, "
+                        f"51 atoms, n={cfg['n']}, {cfg['arch']} net hidden {cfg['hidden']}, {ACTIONS} actions",
+            "global_batch": cfg["B"] * gpus, "parallelism": f"dp{gpus} (independent replay per rank, grad all-reduce)" if gpus > 1 else "single",
+            "l2": "no explicit flush: a step touches ~0.5 GB (parameters, Adam state, noise, activations) of distinct "
+                  "addresses plus random frames of a 7 GB ring, against a 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(cfg, P, noisy_elems):
+    """SURVEY.md 8(d) per-launch algorithmic bytes of each hand-written kernel."""
+    B, n, H, F, Z, A = cfg["B"], cfg["n"], 4, 7056, 51, ACTIONS
+    cap = cfg["cap"]
+    L = (cap - 1).bit_length()
+    return {
+        "tree_sample": B * (L + 1) * 4 + B * 20,
+        "gather": B * min(H + n, 2 * H) * F + B * ((H + n) * 4 + n * 4 + 5) + 2 * B * H * F * 4 + B * 16,
+        "c51": 3 * B * A * Z * 4 + B * 20 + Z * 4 + B * A * Z * 4 + B * 8,
+        "tree_update": B * 12 + B * 4 + B * L * 12,
+        "noisy_resample": noisy_elems * 4,          # per net
+        "sqnorm": P * 4,                            # read grad
+        "clip_adam": 7 * P * 4,                     # read p,g,m,v ; write p,m,v
+        "append": F * 4 + F + 13 + L * 8,
+    }
+
+
+def ours(opts, cfg, rank, world, local):
+    import torch
+
+    from rainbow_b200 import _lib
+    from rainbow_b200.agent import Agent
+    from rainbow_b200.dist import GradSync, shard_seed
+    from rainbow_b200.memory import ReplayMemory
+
+    torch.backends.cudnn.allow_tf32 = False        # the reference computes in true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(shard_seed(0, rank))
+    np.random.seed(123 + rank)
+    args = make_args(cfg, dev)
+    cap, B = cfg["cap"], cfg["B"]
+
+    mem = ReplayMemory(args, cap, seed=shard_seed(17, rank))
+    meta = synthetic_meta(cap, 1 + rank)
+    tr = mem.transitions
+    tr.load_arrays(timestep=meta["timestep"], action=meta["action"], reward=meta["reward"], nonterminal=meta["nonterminal"],
+                   index=meta["head"], full=True, t_episode=int(meta["timestep"][meta["head"] - 1]) + 1)
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+    for s in range(0, cap, 65536):
+        e = min(cap, s + 65536)
+        tr.frames[s:e] = torch.randint(0, 256, (e - s, 7056), dtype=torch.uint8, device=dev, generator=gen)
+    pri = torch.from_numpy(meta["priority"]).to(dev)
+    leaf = torch.arange(cap, device=dev) + tr.tree_start
+    for s in range(0, cap, 1024):
+        tr.update(leaf[s:s + 1024], pri[s:s + 1024])
+    agent = Agent(args, FakeEnv())
+    sync = GradSync()
+
+    def step():
+        agent.reset_noise()
+        agent.learn(mem)
+
+    def barrier():
+        if sync.enabled:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        sync.max_(ms)
+        barrier()
+        return float(ms.item())
+
+    W, K = max(3, opts.warmup), opts.steps
+    for _ in range(Agent.GRAPH_WARMUP + 2):   # eager warm-up + graph capture happen here, outside any timing
+        step()
+    for _ in range(W):
+        step()
+    mem.check_last_sample()
+
+    if opts.profile_steps:   # ncu window (use with `ncu --profile-from-start off`): numbers under a profiler are never reported
+        mode = opts.profile_mode
+        if mode == "eager":
+            agent.use_cuda_graph = False
+            step()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        for i in range(opts.profile_steps):
+            if mode == "e2e":
+                for j in range(REPLAY_FREQUENCY):
+                    mem.append(torch.rand(4, 84, 84).pin_memory(), j, 0.0, False)
+            step()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        return
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- value: inputs resident in HBM, K updates --------------------------------------------------
+    ms_value = timed(lambda i: step(), K)
+    # ---- e2e: public API with host frames ------------------------------------------------------------
+    host_frames = [torch.rand(4, 84, 84).pin_memory() for _ in range(8)]
+    loss_host = torch.empty(B, dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        for j in range(REPLAY_FREQUENCY):
+            mem.append(host_frames[(i + j) % 8], (i + j) % ACTIONS, float((i % 3) - 1), (i * 4 + j) % 1000 == 999)
+        step()
+        loss_host.copy_(agent.last_loss, non_blocking=False)  # D2H read of the step's result (syncs, like agent.py:100)
+
+    for i in range(W):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, K)
+    clocks = sampler.finish()
+    mem.check_last_sample()
+    assert np.isfinite(loss_host.numpy()).all()
+
+    # ---- per-kernel durations: eager pass, CUDA events around every hand-written kernel -------------------
+    agent.use_cuda_graph = False
+    for _ in range(3):
+        step()
+    with _lib.KernelTimer() as kt:
+        for i in range(min(K, 100)):
+            for j in range(REPLAY_FREQUENCY if i % 10 == 0 else 0):
+                mem.append(host_frames[j], j, 0.0, False)
+            step()
+        torch.cuda.synchronize(dev)
+    agent.use_cuda_graph = True
+
+    if rank != 0:
+        return
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    P = agent.optimiser.numel
+    noisy = sum(m.weight_epsilon.numel() + m.bias_epsilon.numel() for m in agent.online_net.noisy_layers())
+    alg = algorithmic_bytes(cfg, P, noisy)
+    launches_per_step = {"noisy_resample": 2, "tree_sample": 1, "gather": 1, "c51": 1, "sqnorm": 1, "clip_adam": 1, "tree_update": 1}
+    kernels = {}
+    for name, (cnt, us) in kt.result.items():
+        if name in alg:
+            gbs = alg[name] / (us * 1e-6) / 1e9
+            kernels[name] = {"us": round(us, 2), "bytes": alg[name], "GBps": round(gbs, 1), "frac": round(gbs / peak, 4),
+                             "launches_timed": cnt}
+    step_kernel_us = {k: kernels[k]["us"] * launches_per_step.get(k, 0) for k in kernels}
+    dominant = max(step_kernel_us, key=step_kernel_us.get)
+    d = kernels[dominant]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(opts.config, {}).get(dominant)
+    roofline = {"kernel": "k_" + dominant, "bound": "hbm", "achieved": d["GBps"], "peak": peak, "unit": "GB/s", "frac": d["frac"],
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": d["bytes"], "us_per_launch": d["us"],
+                "timing": "CUDA events around each launch on its stream, eager (non-graph) replay of the same step",
+                "kernels": kernels,
+                "own_kernel_us_per_step": round(sum(step_kernel_us.values()), 1)}
+
+    total_updates = K * world
+    value = total_updates / (ms_value * 1e-3)
+    e2e_value = total_updates / (ms_e2e * 1e-3)
+    line = {"metric": "learner updates/sec (batch32, 1M buffer, 51 atoms)", "value": value,
+            "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_value / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(opts.config, cfg, world),
+            "e2e": {"value": e2e_value, "unit": "updates/s", "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": REPLAY_FREQUENCY * 84 * 84 * 4, "d2h_bytes_per_step": B * 4,
+                    "what": f"per step: {REPLAY_FREQUENCY} x mem.append(frame from pinned host memory) + dqn.reset_noise() + dqn.learn(mem) + "
+                            "per-sample loss copied to the host"},
+            # our kernels launched in the timed `value` region: per step 2 x (k_noisy_resample + k_bump_counter) + k_tree_sample
+            # + k_gather + k_c51 + k_sqnorm + k_clip_adam + k_bump_step + k_tree_update = 11
+            "gpu_launches": K * 11,
+            "clocks": clocks, "roofline": roofline}
+    if world == 1 and not opts.no_cpu_baseline:
+        n_cpu = opts.cpu_updates
+        ups, dt, threads = run_cpu_port(cfg, n_cpu, 3, with_appends=True)
+        line["cpu_baseline"] = {"value": ups, "unit": "updates/s", "cores": threads, "kind": "port",
+                                "sample": f"{n_cpu} updates of the same workload (each preceded by {REPLAY_FREQUENCY} appends) after 3 warm-up "
+                                          f"updates, {dt:.1f} s; oracle port: replay in C, nets in torch-CPU"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--cpu-updates", type=int, default=150)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=0, help="run this many steps inside cudaProfilerStart/Stop and exit")
+    ap.add_argument("--profile-mode", default="graph", choices=["graph", "eager", "e2e"])
+    opts = ap.parse_args()
+    cfg = CONFIGS[opts.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if opts.impl == "reference":
+        reference_arm(opts, cfg, rank)
+        return
+    if world > 1:
+        from rainbow_b200.dist import init_from_env
+        init_from_env("nccl")
+    elif opts.gpus > 1:
+        print(f"bench.py: --gpus {opts.gpus} needs torchrun (one rank per GPU); running rank 0 only on one GPU", file=sys.stderr)
+    ours(opts, cfg, rank, world, local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -61,8 +61,20 @@ extern "C" {
 
 typedef void* rb_stream_t; /* cudaStream_t */
 
+/* kernel ids for the optional timing hooks (rb_profile_*) */
+enum {
+  RB_K_TREE_UPDATE = 0, RB_K_TREE_FIND, RB_K_TREE_SAMPLE, RB_K_GATHER, RB_K_ITER_STATES, RB_K_APPEND, RB_K_C51,
+  RB_K_NOISY_RESAMPLE, RB_K_NOISY_COMPOSE, RB_K_SQNORM, RB_K_CLIP_ADAM, RB_KERNEL_COUNT
+};
+
 int rb_abi_version(void);
 const char* rb_last_error(void);
+
+/* Diagnostics (no reference counterpart): when enabled, every kernel launch is bracketed by CUDA events
+ * on its stream (do not enable during CUDA-graph capture).  rb_profile_collect synchronises on the
+ * recorded events of one kernel id, returns their summed duration and count, and clears them. */
+int rb_profile_enable(int on);
+int rb_profile_collect(int kernel_id, double* total_ms, int* launches);
 
 /* memory.py:157-159 ReplayMemory.update_priorities -> :44-48 SegmentTree.update
  * (-> :28-33 _propagate -> :23-25 _update_nodes).

@@ -16,6 +16,8 @@ _vp, _i64, _i32, _f32, _u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uin
 SIGNATURES = {
     "rb_abi_version": (C.c_int, []),
     "rb_last_error": (C.c_char_p, []),
+    "rb_profile_enable": (C.c_int, [_i32]),
+    "rb_profile_collect": (C.c_int, [_i32, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "rb_tree_update": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _f32, _i32, _i32, _vp, _vp, _vp]),
     "rb_tree_find": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
     "rb_tree_sample": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _i32, _vp, _i32, _u64, _vp, _i32, _f32, _vp, _i32,
@@ -77,3 +79,26 @@ def ptr(t):
 def stream():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+KERNEL_IDS = ["tree_update", "tree_find", "tree_sample", "gather", "iter_states", "append", "c51", "noisy_resample",
+              "noisy_compose", "sqnorm", "clip_adam"]  # order of the enum in include/rainbow_b200.h
+
+
+class KernelTimer:
+    """with KernelTimer() as kt: ...eager (non-graph) work... ; kt.result -> {kernel: (launches, mean_us)}"""
+
+    def __enter__(self):
+        check(load().rb_profile_enable(1))
+        return self
+
+    def __exit__(self, *exc):
+        lib = load()
+        check(lib.rb_profile_enable(0))
+        self.result = {}
+        for i, name in enumerate(KERNEL_IDS):
+            ms, n = C.c_double(0.0), C.c_int(0)
+            check(lib.rb_profile_collect(i, C.byref(ms), C.byref(n)))
+            if n.value:
+                self.result[name] = (n.value, 1e3 * ms.value / n.value)
+        return False

@@ -204,6 +204,7 @@ class Agent:
         """Record one whole update (sample -> ... -> priority write-back) into a CUDA graph.  Capturing does
         not execute; the caller replays."""
         ws = _SampleWorkspace(self.batch_size, mem.history, self.device)
+        mem.push_beta()  # outside the capture: a captured fill_ would freeze beta at today's value
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):

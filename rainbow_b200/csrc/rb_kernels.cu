@@ -40,6 +40,41 @@ int check_launch(const char* what) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Optional per-kernel timing (diagnostic; off by default): CUDA events recorded on the launching
+// stream immediately before and after each kernel, read back by rb_profile_collect.
+// ------------------------------------------------------------------------------------------------
+constexpr int PROF_SLOTS = 2048;
+struct ProfKernel {
+  cudaEvent_t e0[PROF_SLOTS], e1[PROF_SLOTS];
+  int created = 0, used = 0;
+};
+bool g_prof_on = false;
+ProfKernel g_prof[RB_KERNEL_COUNT];
+
+struct ProfScope {
+  cudaStream_t st;
+  ProfKernel* k = nullptr;
+  ProfScope(int id, cudaStream_t stream) : st(stream) {
+    if (!g_prof_on) return;
+    ProfKernel* pk = &g_prof[id];
+    if (pk->used >= PROF_SLOTS) return;
+    if (pk->used >= pk->created) {
+      cudaEventCreate(&pk->e0[pk->created]);
+      cudaEventCreate(&pk->e1[pk->created]);
+      pk->created++;
+    }
+    k = pk;
+    cudaEventRecord(k->e0[k->used], st);
+  }
+  ~ProfScope() {
+    if (k) {
+      cudaEventRecord(k->e1[k->used], st);
+      k->used++;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based RNG (Salmon et al. 2011), used for the device-side draws.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
@@ -927,14 +962,37 @@ extern "C" {
 
 int rb_abi_version(void) { return RB_ABI_VERSION; }
 
+int rb_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return RB_OK;
+}
+
+int rb_profile_collect(int kernel_id, double* total_ms, int* launches) {
+  if (kernel_id < 0 || kernel_id >= RB_KERNEL_COUNT || !total_ms || !launches) return fail(RB_ERR_INVAL, "rb_profile_collect: bad argument");
+  ProfKernel* k = &g_prof[kernel_id];
+  double t = 0.0;
+  for (int i = 0; i < k->used; ++i) {
+    float ms = 0.0f;
+    cudaError_t e = cudaEventSynchronize(k->e1[i]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, k->e0[i], k->e1[i]);
+    if (e != cudaSuccess) return fail(RB_ERR_CUDA, cudaGetErrorString(e));
+    t += ms;
+  }
+  *total_ms = t;
+  *launches = k->used;
+  k->used = 0;
+  return RB_OK;
+}
+
 const char* rb_last_error(void) { return g_err; }
 
 int rb_tree_update(float* tree, int64_t tree_start, int64_t size, const int64_t* tree_idx, const float* raw_priority,
                    float omega, int omega_is_applied, int B, float* running_max, int32_t* status, rb_stream_t stream) {
   if (!tree || !tree_idx || !raw_priority || !running_max) return fail(RB_ERR_INVAL, "rb_tree_update: null pointer");
   if (B <= 0 || size <= 0 || (size & 1)) return fail(RB_ERR_INVAL, "rb_tree_update: B > 0 and an even size are required");
-  k_tree_update<<<1, UPD_THREADS, 0, (cudaStream_t)stream>>>(tree, tree_start, size, tree_idx, raw_priority, omega,
-                                                             omega_is_applied, B, running_max, status);
+  { ProfScope prof_(RB_K_TREE_UPDATE, (cudaStream_t)stream);
+    k_tree_update<<<1, UPD_THREADS, 0, (cudaStream_t)stream>>>(tree, tree_start, size, tree_idx, raw_priority, omega,
+                                                             omega_is_applied, B, running_max, status); }
   return check_launch("rb_tree_update");
 }
 
@@ -944,7 +1002,8 @@ int rb_tree_find(const float* tree, int64_t tree_start, int64_t size, const doub
   if (B <= 0 || size <= 0) return fail(RB_ERR_INVAL, "rb_tree_find: B and size must be positive");
   int ctas = (B + 31) / 32;
   if (ctas > 148) ctas = 148;
-  k_tree_find<<<ctas, SAMPLE_THREADS, 0, (cudaStream_t)stream>>>(tree, tree_start, size, values, B, probs, data_idx, tree_idx);
+  { ProfScope prof_(RB_K_TREE_FIND, (cudaStream_t)stream);
+    k_tree_find<<<ctas, SAMPLE_THREADS, 0, (cudaStream_t)stream>>>(tree, tree_start, size, values, B, probs, data_idx, tree_idx); }
   return check_launch("rb_tree_find");
 }
 
@@ -958,9 +1017,10 @@ int rb_tree_sample(const float* tree, int64_t tree_start, int64_t size, const in
   if (u01 == nullptr && rng_counter == nullptr) return fail(RB_ERR_INVAL, "rb_tree_sample: need u01 or rng_counter");
   if ((u01 != nullptr && u01_attempts <= 0) || (u01 == nullptr && max_attempts <= 0))
     return fail(RB_ERR_INVAL, "rb_tree_sample: attempts must be positive");
-  k_tree_sample<<<1, SAMPLE_THREADS, 0, (cudaStream_t)stream>>>(
+  { ProfScope prof_(RB_K_TREE_SAMPLE, (cudaStream_t)stream);
+    k_tree_sample<<<1, SAMPLE_THREADS, 0, (cudaStream_t)stream>>>(
       tree, tree_start, size, ring_state, n, history, u01, u01_attempts, seed, (unsigned long long*)rng_counter, B, beta,
-      beta_dev, max_attempts, probs, data_idx, tree_idx, weights, status);
+      beta_dev, max_attempts, probs, data_idx, tree_idx, weights, status); }
   return check_launch("rb_tree_sample");
 }
 
@@ -984,9 +1044,10 @@ int rb_gather(const uint8_t* frames, const int32_t* timestep, const int32_t* act
   const int used = (history + n < 2 * history) ? history + n : 2 * history;
   const int split = gather_split(used * B);
   dim3 grid(used * split, B);
-  k_gather<<<grid, GATHER_THREADS, 0, (cudaStream_t)stream>>>(frames, timestep, action, reward, nonterminal, size, data_idx,
+  { ProfScope prof_(RB_K_GATHER, (cudaStream_t)stream);
+    k_gather<<<grid, GATHER_THREADS, 0, (cudaStream_t)stream>>>(frames, timestep, action, reward, nonterminal, size, data_idx,
                                                               B, history, n, gamma_pow, states, next_states, actions,
-                                                              returns, nonterminals, split);
+                                                              returns, nonterminals, split); }
   return check_launch("rb_gather");
 }
 
@@ -996,7 +1057,8 @@ int rb_iter_states(const uint8_t* frames, const int32_t* timestep, int64_t size,
   if (count <= 0 || history <= 0 || history > RB_MAX_WINDOW || count > 65535)
     return fail(RB_ERR_RANGE, "rb_iter_states: count/history out of range");
   dim3 grid(history, count);
-  k_iter_states<<<grid, GATHER_THREADS, 0, (cudaStream_t)stream>>>(frames, timestep, size, first, history, out);
+  { ProfScope prof_(RB_K_ITER_STATES, (cudaStream_t)stream);
+    k_iter_states<<<grid, GATHER_THREADS, 0, (cudaStream_t)stream>>>(frames, timestep, size, first, history, out); }
   return check_launch("rb_iter_states");
 }
 
@@ -1007,9 +1069,10 @@ int rb_append(float* tree, int64_t tree_start, int64_t size, uint8_t* frames, in
     return fail(RB_ERR_INVAL, "rb_append: null pointer");
   if (size <= 0 || (size & 1)) return fail(RB_ERR_INVAL, "rb_append: an even size is required");
   if (((uintptr_t)state_last_frame & 15) != 0) return fail(RB_ERR_INVAL, "rb_append: state_last_frame must be 16-byte aligned");
-  k_append<<<1, APPEND_THREADS, 0, (cudaStream_t)stream>>>(tree, tree_start, size, frames, timestep, action, reward,
+  { ProfScope prof_(RB_K_APPEND, (cudaStream_t)stream);
+    k_append<<<1, APPEND_THREADS, 0, (cudaStream_t)stream>>>(tree, tree_start, size, frames, timestep, action, reward,
                                                            nonterminal, ring_state, running_max, state_last_frame,
-                                                           action_value, reward_value, terminal);
+                                                           action_value, reward_value, terminal); }
   return check_launch("rb_append");
 }
 
@@ -1023,9 +1086,10 @@ int rb_c51_loss_grad(const float* q_online_s, const float* q_online_ns, const fl
   if (B <= 0 || A <= 0 || Z <= 1) return fail(RB_ERR_INVAL, "rb_c51_loss_grad: B, A > 0 and Z > 1 are required");
   if (Z > RB_MAX_ATOMS) return fail(RB_ERR_RANGE, "rb_c51_loss_grad: Z exceeds RB_MAX_ATOMS");
   const int ctas = (B + C51_WARPS - 1) / C51_WARPS;
-  k_c51<<<ctas, C51_WARPS * 32, 0, (cudaStream_t)stream>>>(q_online_s, q_online_ns, q_target_ns, actions, returns,
+  { ProfScope prof_(RB_K_C51, (cudaStream_t)stream);
+    k_c51<<<ctas, C51_WARPS * 32, 0, (cudaStream_t)stream>>>(q_online_s, q_online_ns, q_target_ns, actions, returns,
                                                           nonterminals, weights, support, vmin, vmax, delta_z, gamma_n, B,
-                                                          A, Z, loss, grad_q_online_s, m_out, astar_out);
+                                                          A, Z, loss, grad_q_online_s, m_out, astar_out); }
   return check_launch("rb_c51_loss_grad");
 }
 
@@ -1066,8 +1130,9 @@ int rb_noisy_resample(float* const* weight_eps, float* const* bias_eps, const in
     cudaError_t e = cudaFuncSetAttribute(k_noisy_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(RB_ERR_CUDA, cudaGetErrorString(e));
   }
-  k_noisy_resample<<<ctas, NOISY_THREADS, smem, (cudaStream_t)stream>>>(plan, x_in, x_out, seed,
-                                                                       (unsigned long long*)rng_counter);
+  { ProfScope prof_(RB_K_NOISY_RESAMPLE, (cudaStream_t)stream);
+    k_noisy_resample<<<ctas, NOISY_THREADS, smem, (cudaStream_t)stream>>>(plan, x_in, x_out, seed,
+                                                                       (unsigned long long*)rng_counter); }
   int rc = check_launch("rb_noisy_resample");
   if (rc != RB_OK) return rc;
   if (x_in == nullptr) {
@@ -1083,7 +1148,8 @@ int rb_noisy_compose(const float* mu, const float* sigma, const float* eps, int6
   int64_t ctas = (count / 4 + 255) / 256;
   if (ctas < 1) ctas = 1;
   if (ctas > 148 * 8) ctas = 148 * 8;
-  k_noisy_compose<<<(int)ctas, 256, 0, (cudaStream_t)stream>>>(mu, sigma, eps, count, out);
+  { ProfScope prof_(RB_K_NOISY_COMPOSE, (cudaStream_t)stream);
+    k_noisy_compose<<<(int)ctas, 256, 0, (cudaStream_t)stream>>>(mu, sigma, eps, count, out); }
   return check_launch("rb_noisy_compose");
 }
 
@@ -1096,11 +1162,13 @@ int rb_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg
     return fail(RB_ERR_INVAL, "rb_clip_adam: null pointer");
   if (P <= 0) return fail(RB_ERR_INVAL, "rb_clip_adam: P must be positive");
   const int ctas = adam_ctas(P);
-  k_sqnorm<<<ctas, ADAM_THREADS, 0, (cudaStream_t)stream>>>(grad, P, grad_scale, partial_sums);
+  { ProfScope prof_(RB_K_SQNORM, (cudaStream_t)stream);
+    k_sqnorm<<<ctas, ADAM_THREADS, 0, (cudaStream_t)stream>>>(grad, P, grad_scale, partial_sums); }
   int rc = check_launch("rb_clip_adam(norm)");
   if (rc != RB_OK) return rc;
-  k_clip_adam<<<ctas, ADAM_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, P, grad_scale, max_norm, lr,
-                                                               beta1, beta2, eps, step_count, partial_sums, ctas, norm_out);
+  { ProfScope prof_(RB_K_CLIP_ADAM, (cudaStream_t)stream);
+    k_clip_adam<<<ctas, ADAM_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, P, grad_scale, max_norm, lr,
+                                                               beta1, beta2, eps, step_count, partial_sums, ctas, norm_out); }
   rc = check_launch("rb_clip_adam");
   if (rc != RB_OK) return rc;
   k_bump_step<<<1, 1, 0, (cudaStream_t)stream>>>(step_count);

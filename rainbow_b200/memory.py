@@ -250,7 +250,6 @@ class ReplayMemory:
     def _launch_sample(self, ws, u01=None, attempts=0):
         tr = self.transitions
         L = self._lib
-        self.push_beta()
         _lib.check(L.rb_tree_sample(
             _lib.ptr(tr.tree), tr.tree_start, tr.size, _lib.ptr(tr.ring_state), self.n, self.history,
             _lib.ptr(u01), attempts, self.seed, _lib.ptr(self._rng_counter), ws.B, float(self.priority_weight),
@@ -266,7 +265,8 @@ class ReplayMemory:
             _lib.ptr(ws.returns), _lib.ptr(ws.nonterminals), _lib.stream()))
 
     def sample_into(self, ws):
-        """Device-RNG sample into caller-owned buffers: two launches, no synchronisation (graph capturable)."""
+        """Device-RNG sample into caller-owned buffers: two launches, no synchronisation (graph capturable).
+        The caller is responsible for push_beta() (outside any graph capture)."""
         self._launch_sample(ws)
         self._launch_gather(ws)
         self._last = ws
@@ -276,6 +276,7 @@ class ReplayMemory:
         """memory.py:148-155.  Returns (tree_idxs, states, actions, returns, next_states, nonterminals, weights),
         all device tensors (the reference returns tree_idxs as numpy; update_priorities takes either)."""
         ws = _SampleWorkspace(int(batch_size), self.history, self.device)
+        self.push_beta()
         if self.rng == "numpy":
             # consume the legacy global generator exactly like np.random.uniform(0, seg, [B]) does
             for _ in range(100000):
