@@ -61,6 +61,26 @@ def synthetic_meta(cap, seed):
                 priority=(rs.uniform(0, 1, cap) ** 0.5 + 1e-3).astype(np.float32), head=12345 % cap)
 
 
+T0 = time.time()
+
+
+def log(*a):
+    print(f"[bench {time.time() - T0:7.1f}s]", *a, file=sys.stderr, flush=True)
+
+
+def host_threads():
+    """Threads the CPU arm may really use: affinity mask and cgroup CPU quota, not the host's core count
+    (hundreds of OpenMP threads inside a small cgroup quota would crawl)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed regions run."""
@@ -112,12 +132,14 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_cpu_port(cfg, updates, warmup, with_appends, seed=1):
-    """The reference's CPU path (oracle port) on this box's cores: returns updates/s over `updates` updates."""
+def run_cpu_port(cfg, updates, warmup, with_appends, seed=1, budget_s=None):
+    """The reference's CPU path (oracle port) on this box's cores: returns updates/s over at most `updates`
+    updates (fewer if `budget_s` seconds run out first; at least 3)."""
     import torch
 
     from oracle.learner import OracleLearner, OracleReplay
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
+    log(f"cpu port: os.cpu_count={os.cpu_count()} usable threads={host_threads()} torch threads={torch.get_num_threads()}")
     torch.manual_seed(0)
     np.random.seed(123)
     cap = cfg["cap"]
@@ -145,13 +167,19 @@ def run_cpu_port(cfg, updates, warmup, with_appends, seed=1):
         learner.reset_noise()
         learner.learn(mem)
 
+    log("cpu port: ring filled, warm-up")
     for i in range(warmup):
         step(i)
     t0 = time.perf_counter()
-    for i in range(updates):
-        step(warmup + i)
+    done = 0
+    while done < updates:
+        step(warmup + done)
+        done += 1
+        if budget_s is not None and done >= 3 and time.perf_counter() - t0 > budget_s:
+            break
     dt = time.perf_counter() - t0
-    return updates / dt, dt, torch.get_num_threads()
+    log(f"cpu port: {done} updates in {dt:.1f}s")
+    return done / dt, dt, torch.get_num_threads(), done
 
 
 def reference_arm(opts, cfg, rank):
@@ -160,16 +188,15 @@ def reference_arm(opts, cfg, rank):
     if rank != 0:
         return
     per_step = 1  # one update (preceded by its 4 appends) per bench "step", exactly like our arm's e2e step
-    ups, dt, threads = run_cpu_port(cfg, opts.steps * per_step, max(3, opts.warmup), with_appends=True)
-    total = opts.steps * per_step
+    ups, dt, threads, total = run_cpu_port(cfg, opts.steps * per_step, min(5, max(3, opts.warmup)), with_appends=True, budget_s=150)
     line = {"impl": "reference", "metric": "learner updates/sec (batch32, 1M buffer, 51 atoms)", "value": ups,
             "unit": "updates/s", "n_gpus": opts.gpus, "steps": opts.steps, "warmup": opts.warmup,
-            "ms_per_step": 1e3 * dt / opts.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * dt / total, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "gpu_launches": 0,
             "config": workload_config(opts.config, cfg, opts.gpus),
             "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": threads, "kind": "port",
                              "sample": f"{total} updates ({per_step} per bench step), each preceded by {REPLAY_FREQUENCY} appends, "
-                                       f"after {max(3, opts.warmup)} warm-up updates; replay tree/gather in C (oracle), nets in torch-CPU "
+                                       f"after {min(5, max(3, opts.warmup))} warm-up updates; replay tree/gather in C (oracle), nets in torch-CPU "
                                        f"with {threads} threads"},
             "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -232,6 +259,7 @@ def ours(opts, cfg, rank, world, local):
     leaf = torch.arange(cap, device=dev) + tr.tree_start
     for s in range(0, cap, 1024):
         tr.update(leaf[s:s + 1024], pri[s:s + 1024])
+    log("replay filled")
     agent = Agent(args, FakeEnv())
     sync = GradSync()
 
@@ -263,6 +291,7 @@ def ours(opts, cfg, rank, world, local):
     for _ in range(W):
         step()
     mem.check_last_sample()
+    log("warm-up + graph capture done")
 
     if opts.profile_steps:   # ncu window (use with `ncu --profile-from-start off`): numbers under a profiler are never reported
         mode = opts.profile_mode
@@ -284,6 +313,7 @@ def ours(opts, cfg, rank, world, local):
     sampler.start()
     # ---- value: inputs resident in HBM, K updates --------------------------------------------------
     ms_value = timed(lambda i: step(), K)
+    log(f"value region: {ms_value / K:.3f} ms/step")
     # ---- e2e: public API with host frames ------------------------------------------------------------
     host_frames = [torch.rand(4, 84, 84).pin_memory() for _ in range(8)]
     loss_host = torch.empty(B, dtype=torch.float32).pin_memory()
@@ -297,6 +327,7 @@ def ours(opts, cfg, rank, world, local):
     for i in range(W):
         e2e_step(i)
     ms_e2e = timed(e2e_step, K)
+    log(f"e2e region: {ms_e2e / K:.3f} ms/step")
     clocks = sampler.finish()
     mem.check_last_sample()
     assert np.isfinite(loss_host.numpy()).all()
@@ -312,6 +343,7 @@ def ours(opts, cfg, rank, world, local):
             step()
         torch.cuda.synchronize(dev)
     agent.use_cuda_graph = True
+    log("kernel timing pass done")
 
     if rank != 0:
         return
@@ -359,8 +391,7 @@ def ours(opts, cfg, rank, world, local):
             "gpu_launches": K * 11,
             "clocks": clocks, "roofline": roofline}
     if world == 1 and not opts.no_cpu_baseline:
-        n_cpu = opts.cpu_updates
-        ups, dt, threads = run_cpu_port(cfg, n_cpu, 3, with_appends=True)
+        ups, dt, threads, n_cpu = run_cpu_port(cfg, opts.cpu_updates, 3, with_appends=True, budget_s=25)
         line["cpu_baseline"] = {"value": ups, "unit": "updates/s", "cores": threads, "kind": "port",
                                 "sample": f"{n_cpu} updates of the same workload (each preceded by {REPLAY_FREQUENCY} appends) after 3 warm-up "
                                           f"updates, {dt:.1f} s; oracle port: replay in C, nets in torch-CPU"}
