@@ -1,0 +1,193 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports every declared symbol, argument
+validation answers without a GPU, the product refuses to run without CUDA (no CPU fallback), format-exchange
+helpers, model layout/initialisation parity with the reference recipe, and the multi-rank gradient exchange
+(world_size 2, gloo)."""
+import argparse
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def make_args(**kw):
+    d = dict(device=torch.device("cpu"), history_length=4, discount=0.99, multi_step=3, priority_weight=0.4,
+             priority_exponent=0.5, atoms=51, V_min=-10.0, V_max=10.0, batch_size=32, norm_clip=10.0, model=None,
+             learning_rate=6.25e-5, adam_eps=1.5e-4, architecture="canonical", hidden_size=512, noisy_std=0.1)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def test_abi_exports_every_declared_symbol():
+    from rainbow_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "rainbow_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|const char\*)\s+(rb_\w+)\s*\(", header, flags=re.M))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), "python binding table and header disagree"
+    for name in declared:
+        assert hasattr(lib, name), f"librainbow_b200.so does not export {name}"
+    assert lib.rb_abi_version() == 1
+    assert lib.rb_clip_adam_scratch_elems() > 0
+
+
+def test_abi_argument_validation_without_gpu():
+    """Bad arguments are rejected on the host before any launch, with errno-style codes."""
+    from rainbow_b200 import _lib
+    lib = _lib.load()
+    one = C.c_void_p(8)  # never dereferenced: validation fails first
+    assert lib.rb_tree_update(None, 7, 8, one, one, 0.5, 0, 4, one, None, None) == -22
+    assert b"null" in lib.rb_last_error()
+    assert lib.rb_tree_update(one, 7, 7, one, one, 0.5, 0, 4, one, None, None) == -22          # odd size
+    assert lib.rb_tree_sample(one, 7, 8, one, 3, 4, None, 0, 1, None, 4, 0.4, None, 8, one, one, one, one, one, None) == -22
+    assert lib.rb_gather(one, one, one, one, one, 8, one, 4, 40, 30, one, one, one, one, one, one, None) == -34  # window > 64
+    assert lib.rb_c51_loss_grad(one, one, one, one, one, one, one, one, -10.0, 10.0, 0.4, 0.97, 4, 6, 200, one, one, None,
+                                None, None) == -34                                               # atoms > 128
+    assert lib.rb_noisy_resample(None, None, None, None, 4, None, None, 1, None, None) == -22
+    assert lib.rb_clip_adam(one, one, one, one, 0, 1.0, 10.0, 1e-4, 0.9, 0.999, 1e-4, one, one, None, None) == -22
+    tot, n = C.c_double(), C.c_int()
+    assert lib.rb_profile_collect(99, C.byref(tot), C.byref(n)) == -22
+
+
+def test_no_cpu_fallback():
+    from rainbow_b200 import RainbowB200Error, _lib
+    from rainbow_b200.agent import Agent
+    from rainbow_b200.memory import ReplayMemory
+    from rainbow_b200.model import DQN
+
+    class Env:
+        def action_space(self):
+            return 6
+
+    with pytest.raises(RainbowB200Error):
+        ReplayMemory(make_args(), 1000)
+    with pytest.raises(RainbowB200Error):
+        Agent(make_args(), Env())
+    with pytest.raises(RainbowB200Error):
+        DQN(make_args(), 6).reset_noise()
+    with pytest.raises(RainbowB200Error):
+        _lib.ptr(torch.zeros(4))
+
+
+def test_product_never_imports_the_oracle():
+    for fn in os.listdir(os.path.join(ROOT, "rainbow_b200")):
+        if fn.endswith(".py"):
+            src = open(os.path.join(ROOT, "rainbow_b200", fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+    cu = open(os.path.join(ROOT, "rainbow_b200", "csrc", "rb_kernels.cu")).read()
+    assert "rb_oracle" not in cu
+
+
+def test_model_layout_and_init_stream():
+    """Same state_dict keys as the reference and -- because construction consumes the torch RNG in the same
+    order (uniform_ for weight_mu, bias_mu, then two randn draws per NoisyLinear) -- a seed gives the same
+    initial sigma/mu statistics recipe (model.py:25-30)."""
+    from rainbow_b200.model import DQN
+    torch.manual_seed(3)
+    net = DQN(make_args(), 6)
+    sd = net.state_dict()
+    assert sd["fc_h_v.weight_mu"].shape == (512, 3136) and sd["fc_z_a.weight_mu"].shape == (6 * 51, 512)
+    assert sd["convs.0.weight"].shape == (32, 4, 8, 8) and sd["convs.4.weight"].shape == (64, 64, 3, 3)
+    assert torch.allclose(sd["fc_h_v.weight_sigma"], torch.full((512, 3136), 0.1 / 3136 ** 0.5))
+    assert torch.allclose(sd["fc_h_v.bias_sigma"], torch.full((512,), 0.1 / 512 ** 0.5))
+    assert sd["fc_h_v.weight_mu"].abs().max() <= 1 / 3136 ** 0.5
+    # construction noise is rank one: eps_w = eps_out (outer) eps_in, eps_b = eps_out
+    w, b = sd["fc_z_v.weight_epsilon"], sd["fc_z_v.bias_epsilon"]
+    assert torch.allclose(w, torch.outer(b, w[0] / b[0]), atol=1e-6)
+    q = net(torch.rand(2, 4, 84, 84))
+    assert q.shape == (2, 6, 51) and torch.allclose(q.sum(2), torch.ones(2, 6), atol=1e-5)
+    assert torch.allclose(net(torch.zeros(1, 4, 84, 84), log=True).exp().sum(2), torch.ones(1, 6), atol=1e-5)
+    de = DQN(make_args(architecture="data-efficient", hidden_size=256), 4)
+    assert de.fc_h_v.weight_mu.shape == (256, 576)
+    with pytest.raises(ValueError):
+        DQN(make_args(architecture="nope"), 4)
+
+
+def test_reference_format_round_trip():
+    from rainbow_b200.memory import Transition_dtype, reference_fields_to_ring, ring_to_reference_fields
+    rs = np.random.RandomState(0)
+    size = 16
+    state = dict(capacity=size, index=5, full=True, max=2.5, sum_tree=rs.rand(15 + size).astype(np.float32),
+                 frames=rs.randint(0, 256, (size, 7056), dtype=np.uint8), timestep=rs.randint(0, 9, size).astype(np.int32),
+                 action=rs.randint(0, 6, size).astype(np.int32), reward=rs.randn(size).astype(np.float32),
+                 nonterminal=rs.randint(0, 2, size).astype(np.uint8))
+    ref = ring_to_reference_fields(state)
+    assert ref["data"].dtype == Transition_dtype and ref["data"].dtype.itemsize == 7069  # memory.py:7 packed record
+    assert ref["tree_start"] == 15 and ref["sum_tree"].shape == (31,)
+    back = reference_fields_to_ring(ref, t=3)
+    for k in ("frames", "timestep", "action", "reward", "nonterminal"):
+        assert np.array_equal(back[k], state[k]), k
+    assert back["index"] == 5 and back["full"] is True and back["max_value"] == 2.5 and back["t_episode"] == 3
+
+
+def test_segment_tree_rejects_odd_sizes_before_touching_cuda():
+    from rainbow_b200.memory import SegmentTree
+    with pytest.raises(ValueError):
+        SegmentTree(7, "cuda:0")
+
+
+def test_shard_seed_and_single_process_sync():
+    from rainbow_b200.dist import GradSync, shard_seed
+    seeds = {shard_seed(0, r) for r in range(8)} | {shard_seed(1, r) for r in range(8)}
+    assert len(seeds) == 16
+    s = GradSync()
+    assert not s.enabled and s.world_size == 1 and s.rank == 0
+    g = torch.ones(8)
+    assert s.all_reduce_(g) is g and s.broadcast_(g) is g and torch.equal(g, torch.ones(8))
+
+
+_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, sys.argv[1])
+from rainbow_b200.dist import GradSync, init_from_env, shard_seed
+rank, world, local = init_from_env("gloo")
+assert world == 2
+sync = GradSync()
+assert sync.enabled and sync.world_size == 2 and sync.rank == rank
+# identical start: rank 0's parameters win
+p = torch.full((1000,), float(rank + 1))
+sync.broadcast_(p)
+assert torch.equal(p, torch.ones(1000))
+# data-parallel step: every rank has its own gradient, all ranks must end with the same averaged one
+torch.manual_seed(shard_seed(0, rank))
+g = torch.randn(1000)
+mine = g.clone()
+sync.all_reduce_(g)
+torch.manual_seed(shard_seed(0, 1 - rank))
+other = torch.randn(1000)
+assert torch.allclose(g, mine + other)
+avg = g * (1.0 / sync.world_size)          # the 1/world factor the clip+Adam kernel applies (grad_scale)
+p -= 0.1 * avg
+chk = p.clone()
+torch.distributed.all_reduce(chk, op=torch.distributed.ReduceOp.MAX)
+assert torch.equal(chk, p), "ranks diverged"
+t = torch.tensor([float(rank)])
+assert float(sync.max_(t)) == 1.0
+torch.distributed.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_two_rank_gradient_exchange_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = 29600 + os.getpid() % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script), ROOT]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+
+
+def test_bench_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=120, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
