@@ -64,7 +64,8 @@ typedef void* rb_stream_t; /* cudaStream_t */
 /* kernel ids for the optional timing hooks (rb_profile_*) */
 enum {
   RB_K_TREE_UPDATE = 0, RB_K_TREE_FIND, RB_K_TREE_SAMPLE, RB_K_GATHER, RB_K_ITER_STATES, RB_K_APPEND, RB_K_C51,
-  RB_K_NOISY_RESAMPLE, RB_K_NOISY_COMPOSE, RB_K_SQNORM, RB_K_CLIP_ADAM, RB_KERNEL_COUNT
+  RB_K_NOISY_RESAMPLE, RB_K_NOISY_COMPOSE, RB_K_SQNORM, RB_K_CLIP_ADAM, RB_K_HEAD_FC1, RB_K_HEAD_FC2, RB_K_HEAD_LOGITS,
+  RB_K_HEAD_WGRAD2, RB_K_HEAD_DH, RB_K_HEAD_BWD1, RB_K_NOISE_FACTORS, RB_K_C51_DUELING, RB_KERNEL_COUNT
 };
 
 int rb_abi_version(void);
@@ -148,6 +149,64 @@ int rb_c51_loss_grad(const float* q_online_s, const float* q_online_ns, const fl
 int rb_noisy_resample(float* const* weight_eps, float* const* bias_eps, const int* in_features,
                       const int* out_features, int n_layers, const float* x_in, const float* x_out, uint64_t seed,
                       uint64_t* rng_counter, rb_stream_t stream);
+
+/* Materialise weight_epsilon / bias_epsilon (model.py:39-40) from ALREADY SCALED factor vectors
+ * f(eps_in) / f(eps_out) (concatenated over layers like x_in / x_out above): eps_w = f_out (outer) f_in. */
+int rb_noisy_outer(float* const* weight_eps, float* const* bias_eps, const int* in_features, const int* out_features,
+                   int n_layers, const float* f_in, const float* f_out, rb_stream_t stream);
+
+/* model.py:36-38 for every NoisyLinear of a net, WITHOUT the outer product: f_in[n_in] / f_out[n_out] receive
+ * f(eps_in) / f(eps_out) of all layers back to back (layer order).  Same Philox indexing as
+ * rb_noisy_resample: rb_noise_factors + rb_noisy_outer == rb_noisy_resample for equal seed and counter.
+ * x_in / x_out: optional injected raw normals (parity).  *rng_counter += 1 in Philox mode. */
+int rb_noise_factors(float* f_in, int n_in, float* f_out, int n_out, const float* x_in, const float* x_out, uint64_t seed,
+                     uint64_t* rng_counter, rb_stream_t stream);
+
+/* ---- fused factorised-noise dueling head (small batches) -----------------------------------------------
+ * model.py:69-75 minus the conv body:  h_s = relu(x W1_s^T + b1_s), z_s = h_s W2_s^T + b2_s for the value (s=0) and
+ * advantage (s=1) streams, W = mu + sigma * (eps_out (outer) eps_in) composed on the fly from the factor vectors
+ * (model.py:39-44) -- weight_epsilon never has to exist in memory.  All pointers are device pointers; the eight
+ * eps_* pointers are either all given (training mode) or all NULL (eval mode, model.py:45-46).
+ * Requirements: conv_features % 32 == 0, hidden % 64 == 0. */
+typedef struct rb_head_params {
+  const float* w1_mu[2];    const float* w1_sigma[2];   /* [hidden][conv_features]        fc_h_v, fc_h_a */
+  const float* b1_mu[2];    const float* b1_sigma[2];   /* [hidden] */
+  const float* w2_mu[2];    const float* w2_sigma[2];   /* [atoms][hidden], [actions*atoms][hidden]   fc_z_v, fc_z_a */
+  const float* b2_mu[2];    const float* b2_sigma[2];
+  const float* eps_in1[2];  const float* eps_out1[2];   /* f(eps): [conv_features], [hidden] */
+  const float* eps_in2[2];  const float* eps_out2[2];   /* [hidden], [atoms] / [actions*atoms] */
+  int conv_features, hidden, atoms, actions;
+} rb_head_params;
+
+typedef struct rb_head_grads {   /* gradients are OVERWRITTEN (not accumulated) */
+  float* w1_mu[2]; float* w1_sigma[2]; float* b1_mu[2]; float* b1_sigma[2];
+  float* w2_mu[2]; float* w2_sigma[2]; float* b2_mu[2]; float* b2_sigma[2];
+} rb_head_grads;
+
+/* split-K factors used by the head kernels: part1 is float32[s1][M][2*hidden], part2 float32[s2][M][atoms*(1+actions)] */
+int rb_head_splits(int conv_features, int hidden, int* s1, int* s2);
+
+/* Forward over M = m_lo + m_hi rows (x_lo: [m_lo][conv_features], x_hi: [m_hi][conv_features] or NULL).
+ * Writes the split-K partials part1, part2 and (if h != NULL) the hidden activations h[M][2*hidden]
+ * (value stream in columns [0,hidden), advantage stream in [hidden, 2*hidden)). */
+int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const float* x_hi, int m_hi, float* part1, float* h,
+                    float* part2, rb_stream_t stream);
+
+/* q[M][actions][atoms] = zv + za - mean_a(za) (model.py:75) from part2 (+ composed layer-2 bias). */
+int rb_head_logits(const rb_head_params* p, const float* part2, int M, float* q, rb_stream_t stream);
+
+/* Backward for B <= 32 rows: given dz[B][atoms*(1+actions)] (value block first), x[B][conv_features] and h[B][2*hidden]
+ * writes all 16 parameter gradients through `g` and dx[B][conv_features].  dh_scratch: float32[B][2*hidden]. */
+int rb_head_backward(const rb_head_params* p, const rb_head_grads* g, const float* x, const float* h, const float* dz, int B,
+                     float* dh_scratch, float* dx, rb_stream_t stream);
+
+/* rb_c51_loss_grad fed by the fused heads: online part2 has 2B rows (s then s'), target part2 B rows (s');
+ * returns loss[B] and dz[B][atoms*(1+actions)] = d mean(w*loss) / d (z_value | z_advantage) of the online(s) rows. */
+int rb_c51_dueling_loss_grad(const rb_head_params* online, const float* part2_online, const rb_head_params* target,
+                             const float* part2_target, const int64_t* actions, const float* returns,
+                             const float* nonterminals, const float* weights, const float* support, float vmin, float vmax,
+                             float delta_z, float gamma_n, int B, float* loss, float* dz, float* m_out, int64_t* astar_out,
+                             rb_stream_t stream);
 
 /* model.py:43-44 NoisyLinear.forward weight composition W = mu + sigma*eps (elementwise),
  * used for both weights ([out*in]) and biases ([out]). */

@@ -406,7 +406,7 @@ def gen_model_step():
     torch.manual_seed(1)
     np.random.seed(1)
     B, A = 4, 3
-    args = make_args(batch_size=B, architecture="data-efficient", hidden_size=32, multi_step=3)
+    args = make_args(batch_size=B, architecture="data-efficient", hidden_size=64, multi_step=3)
     ag = ref_agent.Agent(args, FakeEnv(A))
     for k, v in ag.online_net.state_dict().items():
         out["sd0." + k] = v.numpy().copy()

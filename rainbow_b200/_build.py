@@ -5,7 +5,8 @@ import subprocess
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
-SRC = os.path.join(PKG, "csrc", "rb_kernels.cu")
+SRCS = [os.path.join(PKG, "csrc", f) for f in ("rb_kernels.cu", "rb_head.cu")]
+DEPS = SRCS + [os.path.join(PKG, "csrc", "rb_internal.cuh")]
 HDR = os.path.join(ROOT, "include", "rainbow_b200.h")
 SO = os.path.join(PKG, "librainbow_b200.so")
 
@@ -24,17 +25,17 @@ def stale():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    return any(os.path.exists(p) and os.path.getmtime(p) > t for p in (SRC, HDR))
+    return any(os.path.exists(p) and os.path.getmtime(p) > t for p in DEPS + [HDR])
 
 
 def build(force=False, verbose=False):
-    """Compile rainbow_b200/csrc/rb_kernels.cu -> rainbow_b200/librainbow_b200.so for sm_100a."""
+    """Compile rainbow_b200/csrc/*.cu -> rainbow_b200/librainbow_b200.so for sm_100a."""
     if not force and not stale():
         return SO
     nvcc = nvcc_path()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build librainbow_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO + ".tmp", SRC]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO + ".tmp"] + SRCS
     subprocess.check_call(cmd)
     os.replace(SO + ".tmp", SO)
     return SO

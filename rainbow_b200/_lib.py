@@ -12,6 +12,20 @@ _lib = None
 
 _vp, _i64, _i32, _f32, _u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64
 
+class HeadParams(C.Structure):
+    """rb_head_params of include/rainbow_b200.h (device pointers of one net's noisy dueling head)."""
+    _fields_ = [(n, _vp * 2) for n in ("w1_mu", "w1_sigma", "b1_mu", "b1_sigma", "w2_mu", "w2_sigma", "b2_mu", "b2_sigma",
+                                        "eps_in1", "eps_out1", "eps_in2", "eps_out2")] + \
+               [(n, C.c_int) for n in ("conv_features", "hidden", "atoms", "actions")]
+
+
+class HeadGrads(C.Structure):
+    """rb_head_grads: where rb_head_backward writes the 16 parameter gradients."""
+    _fields_ = [(n, _vp * 2) for n in ("w1_mu", "w1_sigma", "b1_mu", "b1_sigma", "w2_mu", "w2_sigma", "b2_mu", "b2_sigma")]
+
+
+_hp, _hg = C.POINTER(HeadParams), C.POINTER(HeadGrads)
+
 # name -> (restype, argtypes); must list every symbol declared in include/rainbow_b200.h
 SIGNATURES = {
     "rb_abi_version": (C.c_int, []),
@@ -28,6 +42,14 @@ SIGNATURES = {
     "rb_c51_loss_grad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32, _i32, _i32,
                                    _vp, _vp, _vp, _vp, _vp]),
     "rb_noisy_resample": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _u64, _vp, _vp]),
+    "rb_noisy_outer": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "rb_noise_factors": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _u64, _vp, _vp]),
+    "rb_head_splits": (C.c_int, [_i32, _i32, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "rb_head_forward": (C.c_int, [_hp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "rb_head_logits": (C.c_int, [_hp, _vp, _i32, _vp, _vp]),
+    "rb_head_backward": (C.c_int, [_hp, _hg, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "rb_c51_dueling_loss_grad": (C.c_int, [_hp, _vp, _hp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32,
+                                           _vp, _vp, _vp, _vp, _vp]),
     "rb_noisy_compose": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "rb_clip_adam_scratch_elems": (C.c_int, []),
     "rb_clip_adam": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
@@ -82,7 +104,8 @@ def stream():
 
 
 KERNEL_IDS = ["tree_update", "tree_find", "tree_sample", "gather", "iter_states", "append", "c51", "noisy_resample",
-              "noisy_compose", "sqnorm", "clip_adam"]  # order of the enum in include/rainbow_b200.h
+              "noisy_compose", "sqnorm", "clip_adam", "head_fc1", "head_fc2", "head_logits", "head_wgrad2", "head_dh",
+              "head_bwd1", "noise_factors", "c51_dueling"]  # order of the enum in include/rainbow_b200.h
 
 
 class KernelTimer:

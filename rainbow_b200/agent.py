@@ -3,10 +3,11 @@
 One `learn(mem)` (agent.py:61-100) is:
 
     K1 rb_tree_sample + K2 rb_gather          (mem.sample, memory.py:148-155)
-    3 x DQN.logits (torch: cuDNN / cuBLAS)    (agent.py:66,71,75)
+    3 x conv body (torch: cuDNN)              (agent.py:66,71,75 -> model.py:70-71)
     K6 rb_noisy_resample (target net)         (agent.py:74)
-    K3 rb_c51_loss_grad                       (agent.py:67,72-73,76-96 + softmax halves of model.py:76-79)
-    torch autograd backward from d loss / d logits
+    fused noisy dueling heads (rb_head_forward) on the conv features -- online net on [s; s'], target on s'
+    K3 rb_c51_dueling_loss_grad               (agent.py:67,72-73,76-96 + softmax halves of model.py:76-79 + model.py:75)
+    rb_head_backward (16 head gradients + d conv features), torch autograd backward through the online convs
     [NCCL all-reduce of the flat gradient when world_size > 1]
     K7 rb_clip_adam                           (agent.py:97-98)
     K4 rb_tree_update                         (agent.py:100 -> memory.py:157-159)
@@ -42,6 +43,23 @@ def c51_loss_grad(q_online_s, q_online_ns, q_target_ns, actions, returns, nonter
     return loss, grad
 
 
+def c51_dueling_loss_grad(p_online, part2_online, p_target, part2_target, actions, returns, nonterminals, weights, support,
+                          vmin, vmax, delta_z, gamma_n, m_out=None, astar_out=None):
+    """K3 fed straight by the fused heads' split-K partials (rb_c51_dueling_loss_grad): returns (loss[B],
+    dz[B, Z(1+A)]) with dz = d mean(w*loss) / d (z_value | z_advantage) of the online(s) rows."""
+    import ctypes as C
+    B = actions.shape[0]
+    ncols = p_online.atoms * (1 + p_online.actions)
+    loss = torch.empty(B, dtype=torch.float32, device=actions.device)
+    dz = torch.empty((B, ncols), dtype=torch.float32, device=actions.device)
+    _lib.check(_lib.load().rb_c51_dueling_loss_grad(
+        C.byref(p_online), _lib.ptr(part2_online), C.byref(p_target), _lib.ptr(part2_target), _lib.ptr(actions),
+        _lib.ptr(returns), _lib.ptr(nonterminals), _lib.ptr(weights), _lib.ptr(support), float(vmin), float(vmax),
+        float(delta_z), float(gamma_n), B, _lib.ptr(loss), _lib.ptr(dz), _lib.ptr(m_out), _lib.ptr(astar_out),
+        _lib.stream()))
+    return loss, dz
+
+
 class FusedClipAdam:
     """clip_grad_norm_ + Adam (agent.py:46,97-98) over ONE flat parameter buffer.
 
@@ -52,13 +70,19 @@ class FusedClipAdam:
     ALIGN = 64  # elements
 
     def __init__(self, net, lr, eps, max_norm, betas=(0.9, 0.999)):
-        self.params = [p for p in net.parameters() if p.requires_grad]
+        named = [(n, p) for n, p in net.named_parameters() if p.requires_grad]
+        self.params = [p for _, p in named]
         dev = self.params[0].device
         self.offsets, off = [], 0
-        for p in self.params:
+        self.conv_end = None  # flat offset where the first noisy-head parameter starts (convs come first)
+        for n, p in named:
+            if self.conv_end is None and n.startswith("fc_"):
+                self.conv_end = off
             self.offsets.append(off)
             off += -(-p.numel() // self.ALIGN) * self.ALIGN
         self.numel = off
+        if self.conv_end is None:
+            self.conv_end = off
         self.lr, self.eps, self.max_norm, self.betas = float(lr), float(eps), float(max_norm), betas
         self.flat_param = torch.zeros(off, dtype=torch.float32, device=dev)
         self.flat_grad = torch.zeros(off, dtype=torch.float32, device=dev)
@@ -77,6 +101,10 @@ class FusedClipAdam:
 
     def zero_grad(self):
         self.flat_grad.zero_()
+
+    def zero_conv_grad(self):
+        """Only the conv parameters accumulate through autograd on the fused path; the head kernels overwrite theirs."""
+        self.flat_grad[:self.conv_end].zero_()
 
     def step(self, grad_scale=1.0):
         _lib.check(self._lib.rb_clip_adam(
@@ -138,6 +166,7 @@ class Agent:
             p.requires_grad = False
 
         self.use_cuda_graph = bool(getattr(args, "cuda_graph", True))
+        self.use_fused_head = bool(getattr(args, "fused_head", True))
         self._graph = None
         self._graph_key = None
         self._ws = None
@@ -172,8 +201,40 @@ class Agent:
         torch.save(self.online_net.state_dict(), os.path.join(path, name))
 
     # ---- the update ------------------------------------------------------------------------------
+    def _fused_path(self, B):
+        on = self.online_net
+        return self.use_fused_head and B <= 32 and on.training and on.fused_ok(2 * B) and self.target_net.fused_ok(B)
+
+    def _update_fused(self, batch, target_noise=None):
+        """agent.py:66-98 with the fused head: torch only runs the conv bodies (forward x3, backward x1)."""
+        idxs, states, actions, returns, next_states, nonterminals, weights = batch
+        on, tg = self.online_net, self.target_net
+        B = states.shape[0]
+        x_s = on.features(states)                      # autograd graph: convs only
+        with torch.no_grad():
+            x_ns = on.features(next_states)
+            xs_d = x_s.detach()
+            part2_on, h_on, p_on = on.head().forward(xs_d, x_ns)          # rows [0,B) = s, [B,2B) = s'
+            if target_noise is None:
+                tg.reset_noise()                                            # agent.py:74
+            else:
+                tg.reset_noise(*target_noise)
+            part2_t, _, p_t = tg.head().forward(tg.features(next_states))
+            loss, dz = c51_dueling_loss_grad(p_on, part2_on, p_t, part2_t, actions, returns, nonterminals, weights,
+                                             self.support, self.Vmin, self.Vmax, self.delta_z, self.discount ** self.n)
+            self.optimiser.zero_conv_grad()
+            dh = torch.empty((B, 2 * on.hidden_size), dtype=torch.float32, device=self.device)
+            dx = torch.empty_like(xs_d)
+            on.head().backward(p_on, xs_d, h_on[:B], dz, dh, dx)           # writes the 16 head gradients + dx
+        x_s.backward(dx)
+        self.sync.all_reduce_(self.optimiser.flat_grad)
+        self.optimiser.step(grad_scale=1.0 / self.sync.world_size)
+        return loss
+
     def _update_from_batch(self, batch, target_noise=None):
         """agent.py:66-98 on an already sampled batch; returns per-sample losses (device)."""
+        if self._fused_path(batch[1].shape[0]):
+            return self._update_fused(batch, target_noise)
         idxs, states, actions, returns, next_states, nonterminals, weights = batch
         q_s = self.online_net.logits(states)
         with torch.no_grad():

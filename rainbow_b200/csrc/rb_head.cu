@@ -1,0 +1,678 @@
+// rb_head.cu -- fused factorised-noise dueling head for small learner batches (sm_100a).
+//
+// Replaces, for batch <= 64 rows, the reference's per-forward weight composition + four F.linear calls
+// (model.py:42-46 NoisyLinear.forward, model.py:73-75 DQN.forward head) and their autograd backward:
+//
+//   h_s = relu(x W1_s^T + b1_s),  z_s = h_s W2_s^T + b2_s      for the two streams s in {value, advantage}
+//   W   = mu + sigma * (eps_out (outer) eps_in),  b = b_mu + b_sigma * eps_out         (model.py:39-44)
+//
+// The noisy weights are composed ON THE FLY from the factor vectors while the mu/sigma tiles are staged
+// into shared memory, so neither weight_epsilon (13.6 MB per net) nor a composed W temporary ever
+// exists in HBM, and the skinny (M = 32/64) fp32 GEMMs run on every SM through split-K instead of
+// cuBLAS's 64x64 tiles (8 CTAs).  fp32 FMA throughout (the reference computes in fp32); these GEMMs
+// are weight-bandwidth bound at this batch size, not tensor-core work.
+//
+// Kernels: k_head_fc<MT,LAYER> (forward, split-K partials), k_head_logits (bias + dueling combine),
+//          k_head_wgrad2 / k_head_dh (layer-2 backward), k_head_bwd1 (layer-1 dW + dx, CTA-pair cluster
+//          reducing dx over distributed shared memory), k_noise_factors (Philox factor vectors).
+
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "rainbow_b200.h"
+#include "rb_internal.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int HT = 128;  // threads per CTA
+constexpr int NT = 64;   // output-column tile
+constexpr int KT = 32;   // reduction tile
+constexpr int LDB = NT + 4;
+
+struct HeadDesc {  // device pointers; stream 0 = value, 1 = advantage.  Noise pointers may be null (eval mode).
+  const float* w1_mu[2]; const float* w1_sig[2]; const float* b1_mu[2]; const float* b1_sig[2];
+  const float* w2_mu[2]; const float* w2_sig[2]; const float* b2_mu[2]; const float* b2_sig[2];
+  const float* ei1[2]; const float* eo1[2]; const float* ei2[2]; const float* eo2[2];
+  int K1, H, Z, A;
+};
+
+struct HeadGrads {  // where the parameter gradients are written (overwritten, not accumulated)
+  float* w1_mu[2]; float* w1_sig[2]; float* b1_mu[2]; float* b1_sig[2];
+  float* w2_mu[2]; float* w2_sig[2]; float* b2_mu[2]; float* b2_sig[2];
+};
+
+HeadDesc to_desc(const rb_head_params* p) {
+  HeadDesc d;
+  for (int s = 0; s < 2; ++s) {
+    d.w1_mu[s] = p->w1_mu[s]; d.w1_sig[s] = p->w1_sigma[s]; d.b1_mu[s] = p->b1_mu[s]; d.b1_sig[s] = p->b1_sigma[s];
+    d.w2_mu[s] = p->w2_mu[s]; d.w2_sig[s] = p->w2_sigma[s]; d.b2_mu[s] = p->b2_mu[s]; d.b2_sig[s] = p->b2_sigma[s];
+    d.ei1[s] = p->eps_in1[s]; d.eo1[s] = p->eps_out1[s]; d.ei2[s] = p->eps_in2[s]; d.eo2[s] = p->eps_out2[s];
+  }
+  d.K1 = p->conv_features; d.H = p->hidden; d.Z = p->atoms; d.A = p->actions;
+  return d;
+}
+
+__device__ __forceinline__ int n2_of(const HeadDesc& d, int s) { return s == 0 ? d.Z : d.A * d.Z; }
+__device__ __forceinline__ int col2_of(const HeadDesc& d, int s) { return s == 0 ? 0 : d.Z; }
+
+// ------------------------------------------------------------------------------------------------
+// Forward: C[m][n] (partial over a K slice) = sum_k A[m][k] * W[n][k],  W composed while staging.
+// grid = (n tiles over both streams, k slices, m tiles), block = 128, micro tile (MT/8) x 4.
+// LAYER 1: A = x (two row blocks), N per stream = H, K = K1, out part[ks][m][s*H + n].
+// LAYER 2: A = relu(sum_s' part_in[s'][m][s*H + k] + b1[s][k]), N = Z | A*Z, K = H,
+//          out part[ks][m][col2(s) + n]; the first n tile of each stream also writes h (for backward).
+// ------------------------------------------------------------------------------------------------
+template <int MT, int LAYER>
+__global__ void __launch_bounds__(HT)
+k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, int m_lo, const float* __restrict__ x_hi,
+          int M, const float* __restrict__ part_in, int s_in, float* __restrict__ part_out, float* __restrict__ h_out,
+          int kslice) {
+  constexpr int TM = MT / 8;
+  constexpr int LDA = MT + 4;
+  __shared__ __align__(16) float As[KT][LDA];
+  __shared__ __align__(16) float Bs[KT][LDB];
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int K = (LAYER == 1) ? d.K1 : d.H;
+  const int N0 = (LAYER == 1) ? d.H : d.Z;
+  const int tiles0 = (N0 + NT - 1) / NT;
+  const int s = ((int)blockIdx.x < tiles0) ? 0 : 1;
+  const int n0 = (s == 0 ? (int)blockIdx.x : (int)blockIdx.x - tiles0) * NT;
+  const int Ns = (LAYER == 1) ? d.H : n2_of(d, s);
+  const int ncols = (LAYER == 1) ? 2 * d.H : d.Z + d.A * d.Z;
+  const int colbase = (LAYER == 1) ? s * d.H : col2_of(d, s);
+  const int k_begin = blockIdx.y * kslice, k_end = min(K, k_begin + kslice);
+  const int m0 = blockIdx.z * MT;
+  const float* __restrict__ mu = (LAYER == 1) ? d.w1_mu[s] : d.w2_mu[s];
+  const float* __restrict__ sg = (LAYER == 1) ? d.w1_sig[s] : d.w2_sig[s];
+  const float* __restrict__ ei = (LAYER == 1) ? d.ei1[s] : d.ei2[s];
+  const float* __restrict__ eo = (LAYER == 1) ? d.eo1[s] : d.eo2[s];
+
+  float acc[TM][4];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  constexpr int A_PER = MT * (KT / 4) / HT;  // float4 per thread for the A tile (2 or 4)
+  constexpr int B_PER = NT * (KT / 4) / HT;  // 4
+  float4 ra[A_PER], rmu[B_PER], rsg[B_PER];
+
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < A_PER; ++j) {
+      const int idx = tid + j * HT, row = idx >> 3, k = k0 + (idx & 7) * 4, m = m0 + row;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M && k < k_end) {
+        if (LAYER == 1) {
+          const float* src = (m < m_lo) ? x_lo + (size_t)m * K : x_hi + (size_t)(m - m_lo) * K;
+          v = __ldg(reinterpret_cast<const float4*>(src + k));
+        } else {
+          const int hc = s * d.H + k;
+          for (int sp = 0; sp < s_in; ++sp) {
+            float4 p = __ldg(reinterpret_cast<const float4*>(part_in + ((size_t)sp * M + m) * (2 * d.H) + hc));
+            v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+          }
+          float4 bm = __ldg(reinterpret_cast<const float4*>(d.b1_mu[s] + k));
+          if (d.eo1[s]) {
+            float4 bs = __ldg(reinterpret_cast<const float4*>(d.b1_sig[s] + k));
+            float4 e = __ldg(reinterpret_cast<const float4*>(d.eo1[s] + k));
+            bm.x = fmaf(bs.x, e.x, bm.x); bm.y = fmaf(bs.y, e.y, bm.y); bm.z = fmaf(bs.z, e.z, bm.z); bm.w = fmaf(bs.w, e.w, bm.w);
+          }
+          v.x = fmaxf(v.x + bm.x, 0.f); v.y = fmaxf(v.y + bm.y, 0.f); v.z = fmaxf(v.z + bm.z, 0.f); v.w = fmaxf(v.w + bm.w, 0.f);
+          if (h_out && n0 == 0) *reinterpret_cast<float4*>(h_out + (size_t)m * (2 * d.H) + hc) = v;
+        }
+      }
+      ra[j] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < B_PER; ++j) {
+      const int idx = tid + j * HT, row = idx >> 3, k = k0 + (idx & 7) * 4, n = n0 + row;
+      float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = m4;
+      if (n < Ns && k < k_end) {
+        m4 = __ldg(reinterpret_cast<const float4*>(mu + (size_t)n * K + k));
+        if (ei) s4 = __ldg(reinterpret_cast<const float4*>(sg + (size_t)n * K + k));
+      }
+      rmu[j] = m4;
+      rsg[j] = s4;
+    }
+  };
+  auto store_tile = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < A_PER; ++j) {
+      const int idx = tid + j * HT, row = idx >> 3, kk = (idx & 7) * 4;
+      As[kk + 0][row] = ra[j].x; As[kk + 1][row] = ra[j].y; As[kk + 2][row] = ra[j].z; As[kk + 3][row] = ra[j].w;
+    }
+#pragma unroll
+    for (int j = 0; j < B_PER; ++j) {
+      const int idx = tid + j * HT, row = idx >> 3, kk = (idx & 7) * 4, k = k0 + kk, n = n0 + row;
+      float4 w = rmu[j];
+      if (ei && n < Ns && k < k_end) {  // compose W = mu + sigma * (eps_out[n] * eps_in[k])   (model.py:39,43)
+        const float e = __ldg(eo + n);
+        const float4 e4 = __ldg(reinterpret_cast<const float4*>(ei + k));
+        w.x = fmaf(rsg[j].x, e * e4.x, w.x); w.y = fmaf(rsg[j].y, e * e4.y, w.y);
+        w.z = fmaf(rsg[j].z, e * e4.z, w.z); w.w = fmaf(rsg[j].w, e * e4.w, w.w);
+      }
+      Bs[kk + 0][row] = w.x; Bs[kk + 1][row] = w.y; Bs[kk + 2][row] = w.z; Bs[kk + 3][row] = w.w;
+    }
+  };
+
+  if (k_begin < k_end) {
+    load_tile(k_begin);
+    store_tile(k_begin);
+  }
+  __syncthreads();
+  for (int k0 = k_begin; k0 < k_end; k0 += KT) {
+    const bool more = k0 + KT < k_end;
+    if (more) load_tile(k0 + KT);  // global loads in flight while this tile is consumed
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+      float a[TM];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) {
+        float4 t = *reinterpret_cast<const float4*>(&As[kk][ty * TM + i]);
+        a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+      }
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        acc[i][0] = fmaf(a[i], b.x, acc[i][0]); acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+        acc[i][2] = fmaf(a[i], b.z, acc[i][2]); acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+      }
+    }
+    __syncthreads();
+    if (more) {
+      store_tile(k0 + KT);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    if (m >= M) continue;
+    float* dst = part_out + ((size_t)blockIdx.y * M + m) * ncols + colbase;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < Ns) dst[n] = acc[i][j];
+    }
+  }
+}
+
+// q[m][a][z] = zv[z] + za[a][z] - mean_a za[.][z]  (model.py:73-75), z = sum of split-K partials + composed bias.
+__device__ __forceinline__ float head_z(const HeadDesc& d, const float* __restrict__ part, int s2, int M, int m, int s,
+                                        int j) {  // j = row within stream s
+  const int ncols = d.Z + d.A * d.Z, col = col2_of(d, s) + j;
+  float v = 0.0f;
+  for (int sp = 0; sp < s2; ++sp) v += __ldg(part + ((size_t)sp * M + m) * ncols + col);
+  float b = __ldg(d.b2_mu[s] + j);
+  if (d.eo2[s]) b = fmaf(__ldg(d.b2_sig[s] + j), __ldg(d.eo2[s] + j), b);
+  return v + b;
+}
+
+__global__ void __launch_bounds__(128)
+k_head_logits(const __grid_constant__ HeadDesc d, const float* __restrict__ part2, int s2, int M, float* __restrict__ q) {
+  const int m = blockIdx.x;
+  for (int z = threadIdx.x; z < d.Z; z += blockDim.x) {
+    const float zv = head_z(d, part2, s2, M, m, 0, z);
+    float mean = 0.0f;
+    for (int a = 0; a < d.A; ++a) mean += head_z(d, part2, s2, M, m, 1, a * d.Z + z);
+    mean = mean / (float)d.A;
+    for (int a = 0; a < d.A; ++a)
+      q[((size_t)m * d.A + a) * d.Z + z] = zv + head_z(d, part2, s2, M, m, 1, a * d.Z + z) - mean;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layer-2 backward, weight gradients: g[o][k] = sum_m dz[m][col(o)] * h[m][s*H + k]   (both operands are
+// "reduction-major", so tiles are staged without transposition); g_sigma = g * eps_out[o]*eps_in[k].
+// grid = (o tiles over both streams, H / 64), micro tile 8 (o) x 4 (k), reduction over m in chunks of 32.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HT)
+k_head_wgrad2(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrads g, const float* __restrict__ dz,
+              const float* __restrict__ h, int B) {
+  __shared__ __align__(16) float Ds[32][LDB];  // dz chunk [m][o]
+  __shared__ __align__(16) float Hs[32][LDB];  // h chunk  [m][k]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tiles0 = (d.Z + NT - 1) / NT;
+  const int s = ((int)blockIdx.x < tiles0) ? 0 : 1;
+  const int o0 = (s == 0 ? (int)blockIdx.x : (int)blockIdx.x - tiles0) * NT;
+  const int Ns = n2_of(d, s), colbase = col2_of(d, s), ncols = d.Z + d.A * d.Z;
+  const int k0 = blockIdx.y * NT;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  float bsum = 0.0f;  // bias gradient, threads 0..63 of the k-tile-0 CTAs
+  for (int mb = 0; mb < B; mb += 32) {
+    for (int idx = tid; idx < 32 * NT; idx += HT) {
+      const int mm = idx / NT, c = idx % NT, m = mb + mm;
+      Ds[mm][c] = (m < B && o0 + c < Ns) ? __ldg(dz + (size_t)m * ncols + colbase + o0 + c) : 0.0f;
+      Hs[mm][c] = (m < B && k0 + c < d.H) ? __ldg(h + (size_t)m * (2 * d.H) + s * d.H + k0 + c) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int mm = 0; mm < 32; ++mm) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&Ds[mm][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&Ds[mm][ty * 8 + 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Hs[mm][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] = fmaf(a[i], b.x, acc[i][0]); acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+        acc[i][2] = fmaf(a[i], b.z, acc[i][2]); acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+      }
+    }
+    if (blockIdx.y == 0 && tid < NT)
+      for (int mm = 0; mm < 32; ++mm) bsum += Ds[mm][tid];
+    __syncthreads();
+  }
+  const float* ei = d.ei2[s];
+  const float* eo = d.eo2[s];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int o = o0 + ty * 8 + i;
+    if (o >= Ns) continue;
+    const float e = eo ? __ldg(eo + o) : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx * 4 + j;
+      if (k >= d.H) continue;
+      g.w2_mu[s][(size_t)o * d.H + k] = acc[i][j];
+      g.w2_sig[s][(size_t)o * d.H + k] = ei ? acc[i][j] * (e * __ldg(ei + k)) : 0.0f;
+    }
+  }
+  if (blockIdx.y == 0 && tid < NT && o0 + tid < Ns) {
+    g.b2_mu[s][o0 + tid] = bsum;
+    g.b2_sig[s][o0 + tid] = eo ? bsum * __ldg(eo + o0 + tid) : 0.0f;
+  }
+}
+
+// Layer-2 backward, input gradient with the ReLU mask of layer 1 folded in:
+// dh[m][s*H + k] = (h > 0) * sum_o dz[m][col(o)] * W2_s[o][k].   grid = (H/64, 2), 32 rows per pass.
+__global__ void __launch_bounds__(HT)
+k_head_dh(const __grid_constant__ HeadDesc d, const float* __restrict__ dz, const float* __restrict__ h, int B,
+          float* __restrict__ dh) {
+  __shared__ __align__(16) float As[32][36];    // dz chunk transposed [o][m]
+  __shared__ __align__(16) float Bs[32][LDB];   // composed W2 chunk [o][k]
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int s = blockIdx.y, k0 = blockIdx.x * NT;
+  const int Ns = n2_of(d, s), colbase = col2_of(d, s), ncols = d.Z + d.A * d.Z;
+  const float* ei = d.ei2[s];
+  const float* eo = d.eo2[s];
+  for (int mb = 0; mb < B; mb += 32) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int ob = 0; ob < Ns; ob += 32) {
+      for (int idx = tid; idx < 32 * 32; idx += HT) {
+        const int mm = idx >> 5, oo = idx & 31, m = mb + mm, o = ob + oo;
+        As[oo][mm] = (m < B && o < Ns) ? __ldg(dz + (size_t)m * ncols + colbase + o) : 0.0f;
+      }
+      for (int idx = tid; idx < 32 * (NT / 4); idx += HT) {
+        const int oo = idx >> 4, k = k0 + (idx & 15) * 4, o = ob + oo;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o < Ns && k < d.H) {
+          w = __ldg(reinterpret_cast<const float4*>(d.w2_mu[s] + (size_t)o * d.H + k));
+          if (ei) {
+            const float4 sg = __ldg(reinterpret_cast<const float4*>(d.w2_sig[s] + (size_t)o * d.H + k));
+            const float4 e4 = __ldg(reinterpret_cast<const float4*>(ei + k));
+            const float e = __ldg(eo + o);
+            w.x = fmaf(sg.x, e * e4.x, w.x); w.y = fmaf(sg.y, e * e4.y, w.y);
+            w.z = fmaf(sg.z, e * e4.z, w.z); w.w = fmaf(sg.w, e * e4.w, w.w);
+          }
+        }
+        *reinterpret_cast<float4*>(&Bs[oo][(idx & 15) * 4]) = w;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int oo = 0; oo < 32; ++oo) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[oo][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[oo][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[i][0] = fmaf(av[i], b.x, acc[i][0]); acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
+          acc[i][2] = fmaf(av[i], b.z, acc[i][2]); acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = mb + ty * 4 + i;
+      if (m >= B) continue;
+      const int k = k0 + tx * 4;
+      if (k >= d.H) continue;
+      const size_t off = (size_t)m * (2 * d.H) + s * d.H + k;
+      const float4 hv = __ldg(reinterpret_cast<const float4*>(h + off));
+      float4 o4;
+      o4.x = hv.x > 0.f ? acc[i][0] : 0.f; o4.y = hv.y > 0.f ? acc[i][1] : 0.f;
+      o4.z = hv.z > 0.f ? acc[i][2] : 0.f; o4.w = hv.w > 0.f ? acc[i][3] : 0.f;
+      *reinterpret_cast<float4*>(dh + off) = o4;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layer-1 backward for B <= 32 rows: one pass over W1 produces BOTH the weight gradients
+//   g[o][k] = sum_m dh[m][o] * x[m][k]            (written straight into the flat gradient buffer)
+// and the input gradient  dx[m][k] = sum_s sum_o dh[m][s*H+o] * W1_s[o][k].
+// grid = (K1/32, 2 streams) launched as clusters of 2 CTAs along y: the advantage-stream CTA hands its
+// dx partial to the value-stream CTA through distributed shared memory (fixed order -> deterministic).
+// ------------------------------------------------------------------------------------------------
+constexpr int B1_K = 32;  // k columns per CTA
+constexpr int B1_O = 32;  // rows of W1 per chunk
+
+__global__ void __cluster_dims__(1, 2, 1) __launch_bounds__(HT)
+k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrads g, const float* __restrict__ x,
+            const float* __restrict__ dh, int B, float* __restrict__ dx) {
+  __shared__ __align__(16) float Xs[32][B1_K + 4];    // x slice [m][k]
+  __shared__ __align__(16) float Ds[32][B1_O + 4];    // dh chunk [m][o]
+  __shared__ __align__(16) float DsT[B1_O][32 + 4];   // dh chunk [o][m]
+  __shared__ __align__(16) float Ws[B1_O][B1_K + 4];  // composed W1 chunk [o][k]
+  __shared__ __align__(16) float Red[32][B1_K + 4];   // dx partial handed over the cluster
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, tk = tid & 15, to = tid >> 4;  // micro tile: 4 rows (o or m) x 2 k
+  const int s = blockIdx.y, k0 = blockIdx.x * B1_K, K = d.K1, H = d.H;
+  const float* __restrict__ mu = d.w1_mu[s];
+  const float* __restrict__ sg = d.w1_sig[s];
+  const float* ei = d.ei1[s];
+  const float* eo = d.eo1[s];
+
+  for (int idx = tid; idx < 32 * (B1_K / 4); idx += HT) {
+    const int m = idx >> 3, kk = (idx & 7) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < B) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)m * K + k0 + kk));
+    *reinterpret_cast<float4*>(&Xs[m][kk]) = v;
+  }
+  const float ei0 = ei ? __ldg(ei + k0 + tk * 2) : 0.0f, ei1v = ei ? __ldg(ei + k0 + tk * 2 + 1) : 0.0f;
+
+  float dxa[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dxa[i][0] = dxa[i][1] = 0.0f;
+
+  // register prefetch of the next chunk: 32x32 mu, sigma (2 float4 each per thread) and 32x32 dh (2 float4)
+  float4 pmu[2], psg[2], pdh[2];
+  auto prefetch = [&](int ob) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int idx = tid + j * HT, oo = idx >> 3, kk = (idx & 7) * 4, o = ob + oo;
+      pmu[j] = __ldg(reinterpret_cast<const float4*>(mu + (size_t)o * K + k0 + kk));
+      psg[j] = ei ? __ldg(reinterpret_cast<const float4*>(sg + (size_t)o * K + k0 + kk)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int m = idx >> 3, o4 = (idx & 7) * 4;
+      pdh[j] = (m < B) ? __ldg(reinterpret_cast<const float4*>(dh + (size_t)m * (2 * H) + s * H + ob + o4))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto commit = [&](int ob) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int idx = tid + j * HT, oo = idx >> 3, kk = (idx & 7) * 4, o = ob + oo;
+      float4 w = pmu[j];
+      if (ei) {
+        const float e = __ldg(eo + o);
+        const float4 e4 = __ldg(reinterpret_cast<const float4*>(ei + k0 + kk));
+        w.x = fmaf(psg[j].x, e * e4.x, w.x); w.y = fmaf(psg[j].y, e * e4.y, w.y);
+        w.z = fmaf(psg[j].z, e * e4.z, w.z); w.w = fmaf(psg[j].w, e * e4.w, w.w);
+      }
+      *reinterpret_cast<float4*>(&Ws[oo][kk]) = w;
+      const int m = idx >> 3, o4 = (idx & 7) * 4;
+      *reinterpret_cast<float4*>(&Ds[m][o4]) = pdh[j];
+      DsT[o4 + 0][m] = pdh[j].x; DsT[o4 + 1][m] = pdh[j].y; DsT[o4 + 2][m] = pdh[j].z; DsT[o4 + 3][m] = pdh[j].w;
+    }
+  };
+
+  prefetch(0);
+  commit(0);
+  __syncthreads();
+  for (int ob = 0; ob < H; ob += B1_O) {
+    const bool more = ob + B1_O < H;
+    if (more) prefetch(ob + B1_O);
+    // ---- weight gradient tile [32 o][32 k]: reduction over the batch rows ----
+    float ga[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ga[i][0] = ga[i][1] = 0.0f;
+#pragma unroll 8
+    for (int m = 0; m < 32; ++m) {
+      const float4 a = *reinterpret_cast<const float4*>(&Ds[m][to * 4]);
+      const float2 b = *reinterpret_cast<const float2*>(&Xs[m][tk * 2]);
+      ga[0][0] = fmaf(a.x, b.x, ga[0][0]); ga[0][1] = fmaf(a.x, b.y, ga[0][1]);
+      ga[1][0] = fmaf(a.y, b.x, ga[1][0]); ga[1][1] = fmaf(a.y, b.y, ga[1][1]);
+      ga[2][0] = fmaf(a.z, b.x, ga[2][0]); ga[2][1] = fmaf(a.z, b.y, ga[2][1]);
+      ga[3][0] = fmaf(a.w, b.x, ga[3][0]); ga[3][1] = fmaf(a.w, b.y, ga[3][1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int o = ob + to * 4 + i;
+      const size_t off = (size_t)o * K + k0 + tk * 2;
+      *reinterpret_cast<float2*>(g.w1_mu[s] + off) = make_float2(ga[i][0], ga[i][1]);
+      const float e = ei ? __ldg(eo + o) : 0.0f;
+      *reinterpret_cast<float2*>(g.w1_sig[s] + off) = make_float2(ga[i][0] * (e * ei0), ga[i][1] * (e * ei1v));
+    }
+    if (blockIdx.x == 0 && tid < B1_O) {  // bias gradients of this chunk's rows
+      float bs = 0.0f;
+      for (int m = 0; m < 32; ++m) bs += Ds[m][tid];
+      g.b1_mu[s][ob + tid] = bs;
+      g.b1_sig[s][ob + tid] = eo ? bs * __ldg(eo + ob + tid) : 0.0f;
+    }
+    // ---- input gradient [32 m][32 k]: reduction over this chunk's rows of W1 ----
+#pragma unroll 8
+    for (int oo = 0; oo < B1_O; ++oo) {
+      const float4 a = *reinterpret_cast<const float4*>(&DsT[oo][to * 4]);
+      const float2 b = *reinterpret_cast<const float2*>(&Ws[oo][tk * 2]);
+      dxa[0][0] = fmaf(a.x, b.x, dxa[0][0]); dxa[0][1] = fmaf(a.x, b.y, dxa[0][1]);
+      dxa[1][0] = fmaf(a.y, b.x, dxa[1][0]); dxa[1][1] = fmaf(a.y, b.y, dxa[1][1]);
+      dxa[2][0] = fmaf(a.z, b.x, dxa[2][0]); dxa[2][1] = fmaf(a.z, b.y, dxa[2][1]);
+      dxa[3][0] = fmaf(a.w, b.x, dxa[3][0]); dxa[3][1] = fmaf(a.w, b.y, dxa[3][1]);
+    }
+    __syncthreads();
+    if (more) {
+      commit(ob + B1_O);
+      __syncthreads();
+    }
+  }
+  // ---- dx = value-stream partial + advantage-stream partial, over distributed shared memory ----
+  if (s == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<float2*>(&Red[to * 4 + i][tk * 2]) = make_float2(dxa[i][0], dxa[i][1]);
+  }
+  cluster.sync();
+  if (s == 0) {
+    const float* remote = cluster.map_shared_rank(&Red[0][0], 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = to * 4 + i;
+      if (m < B) {
+        const float2 r = *reinterpret_cast<const float2*>(remote + m * (B1_K + 4) + tk * 2);
+        *reinterpret_cast<float2*>(dx + (size_t)m * K + k0 + tk * 2) = make_float2(dxa[i][0] + r.x, dxa[i][1] + r.y);
+      }
+    }
+  }
+  cluster.sync();  // the remote CTA's shared memory must outlive the reads above
+}
+
+// ------------------------------------------------------------------------------------------------
+// Factor vectors f(eps_in), f(eps_out) of every NoisyLinear of a net: one CTA, same Philox indexing as
+// k_noisy_resample (normal g of stream `which` for draw `ctr`), so factors + outer product == K6.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_noise_factors(float* __restrict__ f_in, int n_in, float* __restrict__ f_out, int n_out, const float* __restrict__ x_in,
+                const float* __restrict__ x_out, uint64_t seed, unsigned long long* rng_counter) {
+  const unsigned long long ctr = rng_counter ? *rng_counter : 0ull;
+  for (int which = 0; which < 2; ++which) {
+    float* dst = which ? f_out : f_in;
+    const float* src = which ? x_out : x_in;
+    const int n = which ? n_out : n_in;
+    if (src) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = rbi::scale_noise(__ldg(src + i));
+    } else {
+      for (int blk = threadIdx.x; blk * 4 < n; blk += blockDim.x) {
+        float4 z = rbi::normal4(seed, ctr, (uint32_t)which, (uint32_t)blk);
+        float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (blk * 4 + q < n) dst[blk * 4 + q] = rbi::scale_noise(zz[q]);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && rng_counter && !x_in) *rng_counter = ctr + 1ull;
+}
+
+int head_check(const rb_head_params* p, const char* who) {
+  if (!p) return rbi::fail(RB_ERR_INVAL, who);
+  for (int s = 0; s < 2; ++s)
+    if (!p->w1_mu[s] || !p->w1_sigma[s] || !p->b1_mu[s] || !p->b1_sigma[s] || !p->w2_mu[s] || !p->w2_sigma[s] ||
+        !p->b2_mu[s] || !p->b2_sigma[s])
+      return rbi::fail(RB_ERR_INVAL, who);
+  const bool noisy = p->eps_in1[0] != nullptr;
+  for (int s = 0; s < 2; ++s)
+    if ((p->eps_in1[s] != nullptr) != noisy || (p->eps_out1[s] != nullptr) != noisy || (p->eps_in2[s] != nullptr) != noisy ||
+        (p->eps_out2[s] != nullptr) != noisy)
+      return rbi::fail(RB_ERR_INVAL, "rb_head: give all eight noise factor vectors or none");
+  if (p->conv_features <= 0 || p->hidden <= 0 || p->atoms <= 1 || p->actions <= 0) return rbi::fail(RB_ERR_INVAL, who);
+  for (int s = 0; s < 2; ++s) {  // float4 accesses
+    const uintptr_t bits = (uintptr_t)p->w1_mu[s] | (uintptr_t)p->w1_sigma[s] | (uintptr_t)p->b1_mu[s] | (uintptr_t)p->b1_sigma[s] |
+                           (uintptr_t)p->w2_mu[s] | (uintptr_t)p->w2_sigma[s] | (uintptr_t)p->eps_in1[s] |
+                           (uintptr_t)p->eps_out1[s] | (uintptr_t)p->eps_in2[s];
+    if (bits & 15) return rbi::fail(RB_ERR_INVAL, "rb_head: weight / bias / factor pointers must be 16-byte aligned");
+  }
+  if (p->conv_features % 32 || p->hidden % 64) return rbi::fail(RB_ERR_RANGE, "rb_head: conv_features % 32 == 0 and hidden % 64 == 0 required");
+  return RB_OK;
+}
+
+void head_splits(int K1, int H, int* s1, int* s2, int* ks1, int* ks2) {
+  // aim for about one wave of 148 SMs for layer 1 (N tiles = 2H/64), slices are multiples of the 32-wide k tile
+  const int ntiles1 = 2 * H / NT;
+  int want = (148 + ntiles1 - 1) / ntiles1;
+  const int kt1 = (K1 + KT - 1) / KT;
+  if (want > kt1) want = kt1;
+  if (want > 16) want = 16;
+  if (want < 1) want = 1;
+  int per = (kt1 + want - 1) / want;
+  *ks1 = per * KT;
+  *s1 = (kt1 + per - 1) / per;
+  const int kt2 = H / KT;
+  int w2 = kt2 < 4 ? kt2 : 4;
+  int per2 = (kt2 + w2 - 1) / w2;
+  *ks2 = per2 * KT;
+  *s2 = (kt2 + per2 - 1) / per2;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rb_head_splits(int conv_features, int hidden, int* s1, int* s2) {
+  if (!s1 || !s2 || conv_features <= 0 || hidden <= 0) return rbi::fail(RB_ERR_INVAL, "rb_head_splits: bad argument");
+  int a, b;
+  head_splits(conv_features, hidden, s1, s2, &a, &b);
+  return RB_OK;
+}
+
+int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const float* x_hi, int m_hi, float* part1, float* h,
+                    float* part2, rb_stream_t stream) {
+  int rc = head_check(p, "rb_head_forward: null pointer or bad size");
+  if (rc != RB_OK) return rc;
+  const int M = m_lo + m_hi;
+  if (!x_lo || m_lo <= 0 || m_hi < 0 || (m_hi > 0 && !x_hi) || !part1 || !part2) return rbi::fail(RB_ERR_INVAL, "rb_head_forward: bad argument");
+  if (M > 65535) return rbi::fail(RB_ERR_RANGE, "rb_head_forward: too many rows");
+  const HeadDesc d = to_desc(p);
+  int s1, s2, ks1, ks2;
+  head_splits(d.K1, d.H, &s1, &s2, &ks1, &ks2);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int MT = (M > 32) ? 64 : 32;
+  const int mt = (M + MT - 1) / MT;
+  {
+    dim3 grid(2 * d.H / NT, s1, mt);
+    rbi::ProfScope prof_(RB_K_HEAD_FC1, st);
+    if (MT == 64) k_head_fc<64, 1><<<grid, HT, 0, st>>>(d, x_lo, m_lo, x_hi, M, nullptr, 0, part1, nullptr, ks1);
+    else k_head_fc<32, 1><<<grid, HT, 0, st>>>(d, x_lo, m_lo, x_hi, M, nullptr, 0, part1, nullptr, ks1);
+  }
+  rc = rbi::check_launch("rb_head_forward(fc1)");
+  if (rc != RB_OK) return rc;
+  {
+    const int tiles = (d.Z + NT - 1) / NT + (d.A * d.Z + NT - 1) / NT;
+    dim3 grid(tiles, s2, mt);
+    rbi::ProfScope prof_(RB_K_HEAD_FC2, st);
+    if (MT == 64) k_head_fc<64, 2><<<grid, HT, 0, st>>>(d, nullptr, 0, nullptr, M, part1, s1, part2, h, ks2);
+    else k_head_fc<32, 2><<<grid, HT, 0, st>>>(d, nullptr, 0, nullptr, M, part1, s1, part2, h, ks2);
+  }
+  return rbi::check_launch("rb_head_forward(fc2)");
+}
+
+int rb_head_logits(const rb_head_params* p, const float* part2, int M, float* q, rb_stream_t stream) {
+  int rc = head_check(p, "rb_head_logits: null pointer or bad size");
+  if (rc != RB_OK) return rc;
+  if (!part2 || !q || M <= 0) return rbi::fail(RB_ERR_INVAL, "rb_head_logits: bad argument");
+  const HeadDesc d = to_desc(p);
+  int s1, s2, ks1, ks2;
+  head_splits(d.K1, d.H, &s1, &s2, &ks1, &ks2);
+  {
+    rbi::ProfScope prof_(RB_K_HEAD_LOGITS, (cudaStream_t)stream);
+    k_head_logits<<<M, 128, 0, (cudaStream_t)stream>>>(d, part2, s2, M, q);
+  }
+  return rbi::check_launch("rb_head_logits");
+}
+
+int rb_head_backward(const rb_head_params* p, const rb_head_grads* gr, const float* x, const float* h, const float* dz, int B,
+                     float* dh_scratch, float* dx, rb_stream_t stream) {
+  int rc = head_check(p, "rb_head_backward: null pointer or bad size");
+  if (rc != RB_OK) return rc;
+  if (!gr || !x || !h || !dz || !dh_scratch || !dx) return rbi::fail(RB_ERR_INVAL, "rb_head_backward: null pointer");
+  if (B <= 0 || B > 32) return rbi::fail(RB_ERR_RANGE, "rb_head_backward: 1 <= B <= 32 required (larger batches use the library GEMM path)");
+  HeadGrads g;
+  for (int s = 0; s < 2; ++s) {
+    if (!gr->w1_mu[s] || !gr->w1_sigma[s] || !gr->b1_mu[s] || !gr->b1_sigma[s] || !gr->w2_mu[s] || !gr->w2_sigma[s] ||
+        !gr->b2_mu[s] || !gr->b2_sigma[s])
+      return rbi::fail(RB_ERR_INVAL, "rb_head_backward: null gradient pointer");
+    g.w1_mu[s] = gr->w1_mu[s]; g.w1_sig[s] = gr->w1_sigma[s]; g.b1_mu[s] = gr->b1_mu[s]; g.b1_sig[s] = gr->b1_sigma[s];
+    g.w2_mu[s] = gr->w2_mu[s]; g.w2_sig[s] = gr->w2_sigma[s]; g.b2_mu[s] = gr->b2_mu[s]; g.b2_sig[s] = gr->b2_sigma[s];
+  }
+  const HeadDesc d = to_desc(p);
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    const int tiles = (d.Z + NT - 1) / NT + (d.A * d.Z + NT - 1) / NT;
+    dim3 grid(tiles, d.H / NT);
+    rbi::ProfScope prof_(RB_K_HEAD_WGRAD2, st);
+    k_head_wgrad2<<<grid, HT, 0, st>>>(d, g, dz, h, B);
+  }
+  rc = rbi::check_launch("rb_head_backward(wgrad2)");
+  if (rc != RB_OK) return rc;
+  {
+    dim3 grid(d.H / NT, 2);
+    rbi::ProfScope prof_(RB_K_HEAD_DH, st);
+    k_head_dh<<<grid, HT, 0, st>>>(d, dz, h, B, dh_scratch);
+  }
+  rc = rbi::check_launch("rb_head_backward(dh)");
+  if (rc != RB_OK) return rc;
+  {
+    dim3 grid(d.K1 / B1_K, 2);
+    rbi::ProfScope prof_(RB_K_HEAD_BWD1, st);
+    k_head_bwd1<<<grid, HT, 0, st>>>(d, g, x, dh_scratch, B, dx);
+  }
+  return rbi::check_launch("rb_head_backward(bwd1)");
+}
+
+int rb_noise_factors(float* f_in, int n_in, float* f_out, int n_out, const float* x_in, const float* x_out, uint64_t seed,
+                     uint64_t* rng_counter, rb_stream_t stream) {
+  if (!f_in || !f_out || n_in <= 0 || n_out <= 0) return rbi::fail(RB_ERR_INVAL, "rb_noise_factors: bad argument");
+  if ((x_in == nullptr) != (x_out == nullptr)) return rbi::fail(RB_ERR_INVAL, "rb_noise_factors: give both x_in and x_out or neither");
+  if (!x_in && !rng_counter) return rbi::fail(RB_ERR_INVAL, "rb_noise_factors: need injected normals or rng_counter");
+  {
+    rbi::ProfScope prof_(RB_K_NOISE_FACTORS, (cudaStream_t)stream);
+    k_noise_factors<<<1, 1024, 0, (cudaStream_t)stream>>>(f_in, n_in, f_out, n_out, x_in, x_out, seed, (unsigned long long*)rng_counter);
+  }
+  return rbi::check_launch("rb_noise_factors");
+}
+
+}  // extern "C"

@@ -20,96 +20,28 @@
 #include <string.h>
 
 #include "rainbow_b200.h"
+#include "rb_internal.cuh"
+
+namespace rbi {
+thread_local char g_err[256] = "";
+char* err_buffer() { return g_err; }
+bool g_prof_on = false;
+ProfKernel g_prof[RB_KERNEL_COUNT];
+bool& prof_on() { return g_prof_on; }
+ProfKernel* prof_table() { return g_prof; }
+}  // namespace rbi
 
 namespace {
 
-thread_local char g_err[256] = "";
-
-int fail(int code, const char* what) {
-  snprintf(g_err, sizeof(g_err), "%s", what);
-  return code;
-}
-
-int check_launch(const char* what) {
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) {
-    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
-    return RB_ERR_CUDA;
-  }
-  return RB_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Optional per-kernel timing (diagnostic; off by default): CUDA events recorded on the launching
-// stream immediately before and after each kernel, read back by rb_profile_collect.
-// ------------------------------------------------------------------------------------------------
-constexpr int PROF_SLOTS = 2048;
-struct ProfKernel {
-  cudaEvent_t e0[PROF_SLOTS], e1[PROF_SLOTS];
-  int created = 0, used = 0;
-};
-bool g_prof_on = false;
-ProfKernel g_prof[RB_KERNEL_COUNT];
-
-struct ProfScope {
-  cudaStream_t st;
-  ProfKernel* k = nullptr;
-  ProfScope(int id, cudaStream_t stream) : st(stream) {
-    if (!g_prof_on) return;
-    ProfKernel* pk = &g_prof[id];
-    if (pk->used >= PROF_SLOTS) return;
-    if (pk->used >= pk->created) {
-      cudaEventCreate(&pk->e0[pk->created]);
-      cudaEventCreate(&pk->e1[pk->created]);
-      pk->created++;
-    }
-    k = pk;
-    cudaEventRecord(k->e0[k->used], st);
-  }
-  ~ProfScope() {
-    if (k) {
-      cudaEventRecord(k->e1[k->used], st);
-      k->used++;
-    }
-  }
-};
-
-// ------------------------------------------------------------------------------------------------
-// Philox4x32-10 counter-based RNG (Salmon et al. 2011), used for the device-side draws.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
-
-// 53-bit unit uniform in [0,1) from two 32-bit words (same construction as numpy's random_sample).
-__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
-  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
-}
-
-// Box-Muller: two 32-bit words -> two standard normals.
-__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
-  float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
-  float u2 = (float)b * 2.3283064365386963e-10f;           // [0,1)
-  float r = sqrtf(-2.0f * logf(u1));
-  float s, c;
-  sincospif(2.0f * u2, &s, &c);
-  return make_float2(r * c, r * s);
-}
-
-// model.py:32-34: f(x) = sign(x) * sqrt(|x|)
-__device__ __forceinline__ float scale_noise(float x) {
-  float s = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f);
-  return __fmul_rn(s, __fsqrt_rn(fabsf(x)));
-}
+using rbi::box_muller;
+using rbi::check_launch;
+using rbi::fail;
+using rbi::normal4;
+using rbi::philox4x32_10;
+using rbi::ProfKernel;
+using rbi::ProfScope;
+using rbi::scale_noise;
+using rbi::u53;
 
 __device__ __forceinline__ int64_t pymod(int64_t a, int64_t m) {
   int64_t r = a % m;
@@ -576,50 +508,57 @@ k_append(float* tree, int64_t tree_start, int64_t size, uint8_t* __restrict__ fr
 // One warp per sample; lane owns atoms z = lane + 32*r.  The projected distribution is built as a
 // GATHER (thread per target atom scans the source atoms in order, l-side terms first, then u-side
 // terms): deterministic and in the reference CPU index_add_ order (agent.py:91-92), no atomics.
+// c51_core works on logit ROWS given by generic pointers (global memory for the plain entry point,
+// warp-private shared memory for the dueling entry point) and returns, per lane, the gradient row
+// g[z] = (w/B)(p*sum(m) - m) of the taken action.
 constexpr int C51_WARPS = 4;
 constexpr int C51_R = RB_MAX_ATOMS / 32;
 
-__global__ void __launch_bounds__(C51_WARPS * 32)
-k_c51(const float* __restrict__ q_on_s, const float* __restrict__ q_on_ns, const float* __restrict__ q_tg_ns,
-      const int64_t* __restrict__ actions, const float* __restrict__ returns, const float* __restrict__ nonterminals,
-      const float* __restrict__ weights, const float* __restrict__ support, float vmin, float vmax, float delta_z,
-      float gamma_n, int B, int A, int Z, float* __restrict__ loss, float* __restrict__ grad, float* __restrict__ m_out,
-      int64_t* __restrict__ astar_out) {
-  __shared__ float s_pt[C51_WARPS][RB_MAX_ATOMS];  // target probabilities p(s', a*)
-  __shared__ float s_b[C51_WARPS][RB_MAX_ATOMS];
-  __shared__ int s_l[C51_WARPS][RB_MAX_ATOMS];
-  __shared__ int s_u[C51_WARPS][RB_MAX_ATOMS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * C51_WARPS + warp;
-  if (i >= B) return;
+struct C51Scratch {  // per warp
+  float pt[RB_MAX_ATOMS];  // target probabilities p(s', a*)
+  float b[RB_MAX_ATOMS];
+  int l[RB_MAX_ATOMS];
+  int u[RB_MAX_ATOMS];
+};
 
+__device__ __forceinline__ void softmax_row(const float* row, int Z, int lane, float (&e)[C51_R], float (&x)[C51_R],
+                                            float& mx, float& sum) {
+  mx = -CUDART_INF_F;
+#pragma unroll
+  for (int r = 0; r < C51_R; ++r) {
+    int z = lane + 32 * r;
+    x[r] = (z < Z) ? row[z] : -CUDART_INF_F;
+    mx = fmaxf(mx, x[r]);
+  }
+  mx = warp_max(mx);
+  sum = 0.0f;
+#pragma unroll
+  for (int r = 0; r < C51_R; ++r) {
+    e[r] = (lane + 32 * r < Z) ? expf(x[r] - mx) : 0.0f;
+    sum = __fadd_rn(sum, e[r]);
+  }
+  sum = warp_sum(sum);
+}
+
+// q_on_ns / q_tg_ns: A rows of Z (row stride Z); q_on_s_act: the row of the taken action.
+__device__ __forceinline__ void c51_core(C51Scratch& sc, int lane, int i, int B, int A, int Z, const float* q_on_ns,
+                                         const float* q_tg_ns, const float* q_on_s_act, float ret, float nonterminal,
+                                         float weight, const float* __restrict__ support, float vmin, float vmax,
+                                         float delta_z, float gamma_n, float* __restrict__ loss, float* __restrict__ m_out,
+                                         int64_t* __restrict__ astar_out, float (&g)[C51_R]) {
   float sup[C51_R];
 #pragma unroll
   for (int r = 0; r < C51_R; ++r) {
     int z = lane + 32 * r;
     sup[r] = (z < Z) ? __ldg(support + z) : 0.0f;
   }
+  float e[C51_R], x[C51_R], mx, sum;
 
   // ---- agent.py:71-73: a* = argmax_a sum_z support_z * softmax(q_online(s'))[a,z] ----
   int best = 0;
   float best_ev = -CUDART_INF_F;
   for (int a = 0; a < A; ++a) {
-    const float* row = q_on_ns + ((size_t)i * A + a) * Z;
-    float x[C51_R], mx = -CUDART_INF_F;
-#pragma unroll
-    for (int r = 0; r < C51_R; ++r) {
-      int z = lane + 32 * r;
-      x[r] = (z < Z) ? __ldg(row + z) : -CUDART_INF_F;
-      mx = fmaxf(mx, x[r]);
-    }
-    mx = warp_max(mx);
-    float e[C51_R], sum = 0.0f;
-#pragma unroll
-    for (int r = 0; r < C51_R; ++r) {
-      e[r] = (lane + 32 * r < Z) ? expf(x[r] - mx) : 0.0f;
-      sum = __fadd_rn(sum, e[r]);
-    }
-    sum = warp_sum(sum);
+    softmax_row(q_on_ns + (size_t)a * Z, Z, lane, e, x, mx, sum);
     float ev = 0.0f;
 #pragma unroll
     for (int r = 0; r < C51_R; ++r) ev = __fadd_rn(ev, __fmul_rn(sup[r], __fdiv_rn(e[r], sum)));
@@ -632,50 +571,17 @@ k_c51(const float* __restrict__ q_on_s, const float* __restrict__ q_on_ns, const
   if (astar_out && lane == 0) astar_out[i] = best;
 
   // ---- agent.py:75-76: target distribution of the selected action ----
-  {
-    const float* row = q_tg_ns + ((size_t)i * A + best) * Z;
-    float x[C51_R], mx = -CUDART_INF_F;
+  softmax_row(q_tg_ns + (size_t)best * Z, Z, lane, e, x, mx, sum);
 #pragma unroll
-    for (int r = 0; r < C51_R; ++r) {
-      int z = lane + 32 * r;
-      x[r] = (z < Z) ? __ldg(row + z) : -CUDART_INF_F;
-      mx = fmaxf(mx, x[r]);
-    }
-    mx = warp_max(mx);
-    float e[C51_R], sum = 0.0f;
-#pragma unroll
-    for (int r = 0; r < C51_R; ++r) {
-      e[r] = (lane + 32 * r < Z) ? expf(x[r] - mx) : 0.0f;
-      sum = __fadd_rn(sum, e[r]);
-    }
-    sum = warp_sum(sum);
-#pragma unroll
-    for (int r = 0; r < C51_R; ++r) {
-      int z = lane + 32 * r;
-      if (z < Z) s_pt[warp][z] = __fdiv_rn(e[r], sum);
-    }
+  for (int r = 0; r < C51_R; ++r) {
+    int z = lane + 32 * r;
+    if (z < Z) sc.pt[z] = __fdiv_rn(e[r], sum);
   }
 
   // ---- agent.py:66-67: log p(s, a) and p(s, a) of the online net ----
-  const int act = (int)actions[i];
   float p_on[C51_R], logp[C51_R];
+  softmax_row(q_on_s_act, Z, lane, e, x, mx, sum);
   {
-    const float* row = q_on_s + ((size_t)i * A + act) * Z;
-    float x[C51_R], mx = -CUDART_INF_F;
-#pragma unroll
-    for (int r = 0; r < C51_R; ++r) {
-      int z = lane + 32 * r;
-      x[r] = (z < Z) ? __ldg(row + z) : -CUDART_INF_F;
-      mx = fmaxf(mx, x[r]);
-    }
-    mx = warp_max(mx);
-    float e[C51_R], sum = 0.0f;
-#pragma unroll
-    for (int r = 0; r < C51_R; ++r) {
-      e[r] = (lane + 32 * r < Z) ? expf(x[r] - mx) : 0.0f;
-      sum = __fadd_rn(sum, e[r]);
-    }
-    sum = warp_sum(sum);
     const float lsum = logf(sum);
 #pragma unroll
     for (int r = 0; r < C51_R; ++r) {
@@ -685,8 +591,7 @@ k_c51(const float* __restrict__ q_on_s, const float* __restrict__ q_on_ns, const
   }
 
   // ---- agent.py:79-86: Tz, b, l, u ----
-  const float ret = __ldg(returns + i);
-  const float scale = __fmul_rn(__ldg(nonterminals + i), gamma_n);
+  const float scale = __fmul_rn(nonterminal, gamma_n);
 #pragma unroll
   for (int r = 0; r < C51_R; ++r) {
     int z = lane + 32 * r;
@@ -697,9 +602,9 @@ k_c51(const float* __restrict__ q_on_s, const float* __restrict__ q_on_ns, const
       int lo = (int)floorf(bb), up = (int)ceilf(bb);
       if (up > 0 && lo == up) lo -= 1;
       if (lo < Z - 1 && lo == up) up += 1;
-      s_b[warp][z] = bb;
-      s_l[warp][z] = lo;
-      s_u[warp][z] = up;
+      sc.b[z] = bb;
+      sc.l[z] = lo;
+      sc.u[z] = up;
     }
   }
   __syncwarp();
@@ -713,9 +618,9 @@ k_c51(const float* __restrict__ q_on_s, const float* __restrict__ q_on_ns, const
     float acc = 0.0f;
     if (k < Z) {
       for (int j = 0; j < Z; ++j)
-        if (s_l[warp][j] == k) acc = __fadd_rn(acc, __fmul_rn(s_pt[warp][j], __fsub_rn((float)s_u[warp][j], s_b[warp][j])));
+        if (sc.l[j] == k) acc = __fadd_rn(acc, __fmul_rn(sc.pt[j], __fsub_rn((float)sc.u[j], sc.b[j])));
       for (int j = 0; j < Z; ++j)
-        if (s_u[warp][j] == k) acc = __fadd_rn(acc, __fmul_rn(s_pt[warp][j], __fsub_rn(s_b[warp][j], (float)s_l[warp][j])));
+        if (sc.u[j] == k) acc = __fadd_rn(acc, __fmul_rn(sc.pt[j], __fsub_rn(sc.b[j], (float)sc.l[j])));
       if (m_out) m_out[(size_t)i * Z + k] = acc;
     }
     m[r] = acc;
@@ -726,15 +631,104 @@ k_c51(const float* __restrict__ q_on_s, const float* __restrict__ q_on_ns, const
   msum = warp_sum(msum);
   if (lane == 0) loss[i] = -ce;  // agent.py:94
 
-  // ---- agent.py:96: d mean(w*loss) / d q_online(s)[i, :, :] ----
-  const float wi = __fdiv_rn(__ldg(weights + i), (float)B);
-  float* g = grad + (size_t)i * A * Z;
-  for (int j = lane; j < A * Z; j += 32) g[j] = 0.0f;
+  // ---- agent.py:96: d mean(w*loss) / d q_online(s)[i, act, :] ----
+  const float wi = __fdiv_rn(weight, (float)B);
+#pragma unroll
+  for (int r = 0; r < C51_R; ++r) g[r] = __fmul_rn(wi, __fsub_rn(__fmul_rn(p_on[r], msum), m[r]));
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(C51_WARPS * 32)
+k_c51(const float* __restrict__ q_on_s, const float* __restrict__ q_on_ns, const float* __restrict__ q_tg_ns,
+      const int64_t* __restrict__ actions, const float* __restrict__ returns, const float* __restrict__ nonterminals,
+      const float* __restrict__ weights, const float* __restrict__ support, float vmin, float vmax, float delta_z,
+      float gamma_n, int B, int A, int Z, float* __restrict__ loss, float* __restrict__ grad, float* __restrict__ m_out,
+      int64_t* __restrict__ astar_out) {
+  __shared__ C51Scratch s_sc[C51_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * C51_WARPS + warp;
+  if (i >= B) return;
+  const int act = (int)actions[i];
+  float g[C51_R];
+  c51_core(s_sc[warp], lane, i, B, A, Z, q_on_ns + (size_t)i * A * Z, q_tg_ns + (size_t)i * A * Z,
+           q_on_s + ((size_t)i * A + act) * Z, __ldg(returns + i), __ldg(nonterminals + i), __ldg(weights + i), support, vmin,
+           vmax, delta_z, gamma_n, loss, m_out, astar_out, g);
+  float* gq = grad + (size_t)i * A * Z;
+  for (int j = lane; j < A * Z; j += 32) gq[j] = 0.0f;
   __syncwarp();
 #pragma unroll
   for (int r = 0; r < C51_R; ++r) {
     int z = lane + 32 * r;
-    if (z < Z) g[(size_t)act * Z + z] = __fmul_rn(wi, __fsub_rn(__fmul_rn(p_on[r], msum), m[r]));
+    if (z < Z) gq[(size_t)act * Z + z] = g[r];
+  }
+}
+
+// Dueling entry point: logits are rebuilt per sample from the fused head's split-K partial outputs
+// (z = sum of partials + composed bias; q[a][z] = zv[z] + za[a][z] - mean_a za[.][z], model.py:73-75) in
+// warp-private shared memory, and the gradient is returned w.r.t. the head outputs:
+// dzv[z] = g[z],  dza[a][z] = g[z] * ([a == act] - 1/A).
+struct DuelSide {  // one network's head output
+  const float* part2;    // [s2][rows][Z + A*Z]
+  const float* b2_mu[2];
+  const float* b2_sig[2];
+  const float* eo2[2];   // null in eval mode
+  int s2, rows;
+};
+
+__device__ __forceinline__ float duel_z(const DuelSide& d, int Z, int A, int row, int s, int j) {
+  const int ncols = Z + A * Z, col = (s == 0 ? 0 : Z) + j;
+  float v = 0.0f;
+  for (int sp = 0; sp < d.s2; ++sp) v += __ldg(d.part2 + ((size_t)sp * d.rows + row) * ncols + col);
+  float b = __ldg(d.b2_mu[s] + j);
+  if (d.eo2[s]) b = fmaf(__ldg(d.b2_sig[s] + j), __ldg(d.eo2[s] + j), b);
+  return v + b;
+}
+
+// fills q[a][z] for a in [0,A) (or only row `only_a` into q[0][z] when only_a >= 0)
+__device__ __forceinline__ void duel_rows(const DuelSide& d, int Z, int A, int row, int lane, float* q, int only_a) {
+  for (int z = lane; z < Z; z += 32) {
+    const float zv = duel_z(d, Z, A, row, 0, z);
+    float mean = 0.0f;
+    for (int a = 0; a < A; ++a) mean += duel_z(d, Z, A, row, 1, a * Z + z);
+    mean = mean / (float)A;
+    if (only_a >= 0) {
+      q[z] = zv + duel_z(d, Z, A, row, 1, only_a * Z + z) - mean;
+    } else {
+      for (int a = 0; a < A; ++a) q[(size_t)a * Z + z] = zv + duel_z(d, Z, A, row, 1, a * Z + z) - mean;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(C51_WARPS * 32)
+k_c51_dueling(const __grid_constant__ DuelSide on, const __grid_constant__ DuelSide tg, const int64_t* __restrict__ actions,
+              const float* __restrict__ returns, const float* __restrict__ nonterminals, const float* __restrict__ weights,
+              const float* __restrict__ support, float vmin, float vmax, float delta_z, float gamma_n, int B, int A, int Z,
+              float* __restrict__ loss, float* __restrict__ dz, float* __restrict__ m_out, int64_t* __restrict__ astar_out) {
+  extern __shared__ __align__(16) float s_dyn[];  // per warp: q_on_ns [A*Z], q_tg [A*Z], q_on_s_act [Z]
+  __shared__ C51Scratch s_sc[C51_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * C51_WARPS + warp;
+  if (i >= B) return;
+  float* q_ns = s_dyn + (size_t)warp * (2 * A * Z + Z);
+  float* q_t = q_ns + A * Z;
+  float* q_s = q_t + A * Z;
+  const int act = (int)actions[i];
+  duel_rows(on, Z, A, B + i, lane, q_ns, -1);  // online(s'): rows B..2B-1 of the batched online pass
+  duel_rows(tg, Z, A, i, lane, q_t, -1);       // target(s')
+  duel_rows(on, Z, A, i, lane, q_s, act);      // online(s), taken action only
+  __syncwarp();
+  float g[C51_R];
+  c51_core(s_sc[warp], lane, i, B, A, Z, q_ns, q_t, q_s, __ldg(returns + i), __ldg(nonterminals + i), __ldg(weights + i),
+           support, vmin, vmax, delta_z, gamma_n, loss, m_out, astar_out, g);
+  float* dzi = dz + (size_t)i * (Z + A * Z);
+  const float inv_a = 1.0f / (float)A;
+#pragma unroll
+  for (int r = 0; r < C51_R; ++r) {
+    const int z = lane + 32 * r;
+    if (z < Z) {
+      dzi[z] = g[r];
+      for (int a = 0; a < A; ++a) dzi[Z + a * Z + z] = g[r] * ((a == act ? 1.0f : 0.0f) - inv_a);
+    }
   }
 }
 
@@ -755,17 +749,9 @@ struct NoisyPlan {
 
 constexpr int NOISY_THREADS = 256;
 
-// Normal number `idx` of stream `which` (0 = eps_in, 1 = eps_out) for draw `ctr`.
-__device__ __forceinline__ float4 normal4(uint64_t seed, unsigned long long ctr, uint32_t which, uint32_t idx4) {
-  uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), idx4, 0x4E4F4953u + which),
-                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-
 __global__ void __launch_bounds__(NOISY_THREADS)
 k_noisy_resample(const __grid_constant__ NoisyPlan plan, const float* __restrict__ x_in, const float* __restrict__ x_out,
-                 uint64_t seed, unsigned long long* rng_counter) {
+                 uint64_t seed, unsigned long long* rng_counter, int prescaled) {
   extern __shared__ __align__(16) float s_in[];  // f(eps_in) of this CTA's layer
   int l = 0;
   while (l + 1 < plan.n && (int)blockIdx.x >= plan.cta_begin[l + 1]) ++l;
@@ -776,7 +762,10 @@ k_noisy_resample(const __grid_constant__ NoisyPlan plan, const float* __restrict
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (x_in) {
-    for (int i = tid; i < in_f; i += NOISY_THREADS) s_in[i] = scale_noise(__ldg(x_in + plan.in_off[l] + i));
+    for (int i = tid; i < in_f; i += NOISY_THREADS) {
+      const float v = __ldg(x_in + plan.in_off[l] + i);
+      s_in[i] = prescaled ? v : scale_noise(v);
+    }
   } else {
     // global normal index g = in_off + i ; Philox block g/4 yields normals 4*(g/4) .. +3
     const int g0 = plan.in_off[l], g1 = g0 + in_f;
@@ -805,7 +794,7 @@ k_noisy_resample(const __grid_constant__ NoisyPlan plan, const float* __restrict
       int q = g & 3;
       xo = q == 0 ? z.x : (q == 1 ? z.y : (q == 2 ? z.z : z.w));
     }
-    const float eo = scale_noise(xo);
+    const float eo = (x_out && prescaled) ? xo : scale_noise(xo);
     if (lane == 0) bias[o] = eo;                       // model.py:40
     float* row = w + (size_t)o * in_f;                 // model.py:39 eps_out (outer) eps_in
     if (vec) {
@@ -963,13 +952,13 @@ extern "C" {
 int rb_abi_version(void) { return RB_ABI_VERSION; }
 
 int rb_profile_enable(int on) {
-  g_prof_on = on != 0;
+  rbi::g_prof_on = on != 0;
   return RB_OK;
 }
 
 int rb_profile_collect(int kernel_id, double* total_ms, int* launches) {
   if (kernel_id < 0 || kernel_id >= RB_KERNEL_COUNT || !total_ms || !launches) return fail(RB_ERR_INVAL, "rb_profile_collect: bad argument");
-  ProfKernel* k = &g_prof[kernel_id];
+  ProfKernel* k = &rbi::g_prof[kernel_id];
   double t = 0.0;
   for (int i = 0; i < k->used; ++i) {
     float ms = 0.0f;
@@ -984,7 +973,7 @@ int rb_profile_collect(int kernel_id, double* total_ms, int* launches) {
   return RB_OK;
 }
 
-const char* rb_last_error(void) { return g_err; }
+const char* rb_last_error(void) { return rbi::g_err; }
 
 int rb_tree_update(float* tree, int64_t tree_start, int64_t size, const int64_t* tree_idx, const float* raw_priority,
                    float omega, int omega_is_applied, int B, float* running_max, int32_t* status, rb_stream_t stream) {
@@ -1093,9 +1082,9 @@ int rb_c51_loss_grad(const float* q_online_s, const float* q_online_ns, const fl
   return check_launch("rb_c51_loss_grad");
 }
 
-int rb_noisy_resample(float* const* weight_eps, float* const* bias_eps, const int* in_features, const int* out_features,
-                      int n_layers, const float* x_in, const float* x_out, uint64_t seed, uint64_t* rng_counter,
-                      rb_stream_t stream) {
+static int noisy_launch(float* const* weight_eps, float* const* bias_eps, const int* in_features, const int* out_features,
+                        int n_layers, const float* x_in, const float* x_out, uint64_t seed, uint64_t* rng_counter,
+                        int prescaled, rb_stream_t stream) {
   if (!weight_eps || !bias_eps || !in_features || !out_features) return fail(RB_ERR_INVAL, "rb_noisy_resample: null pointer");
   if (n_layers <= 0 || n_layers > RB_MAX_NOISY_LAYERS) return fail(RB_ERR_RANGE, "rb_noisy_resample: n_layers out of range");
   if ((x_in == nullptr) != (x_out == nullptr)) return fail(RB_ERR_INVAL, "rb_noisy_resample: give both x_in and x_out or neither");
@@ -1132,7 +1121,7 @@ int rb_noisy_resample(float* const* weight_eps, float* const* bias_eps, const in
   }
   { ProfScope prof_(RB_K_NOISY_RESAMPLE, (cudaStream_t)stream);
     k_noisy_resample<<<ctas, NOISY_THREADS, smem, (cudaStream_t)stream>>>(plan, x_in, x_out, seed,
-                                                                       (unsigned long long*)rng_counter); }
+                                                                       (unsigned long long*)rng_counter, prescaled); }
   int rc = check_launch("rb_noisy_resample");
   if (rc != RB_OK) return rc;
   if (x_in == nullptr) {
@@ -1140,6 +1129,56 @@ int rb_noisy_resample(float* const* weight_eps, float* const* bias_eps, const in
     rc = check_launch("rb_noisy_resample(counter)");
   }
   return rc;
+}
+
+int rb_noisy_resample(float* const* weight_eps, float* const* bias_eps, const int* in_features, const int* out_features,
+                      int n_layers, const float* x_in, const float* x_out, uint64_t seed, uint64_t* rng_counter,
+                      rb_stream_t stream) {
+  return noisy_launch(weight_eps, bias_eps, in_features, out_features, n_layers, x_in, x_out, seed, rng_counter, 0, stream);
+}
+
+int rb_noisy_outer(float* const* weight_eps, float* const* bias_eps, const int* in_features, const int* out_features,
+                   int n_layers, const float* f_in, const float* f_out, rb_stream_t stream) {
+  if (!f_in || !f_out) return fail(RB_ERR_INVAL, "rb_noisy_outer: null factor vectors");
+  return noisy_launch(weight_eps, bias_eps, in_features, out_features, n_layers, f_in, f_out, 0, nullptr, 1, stream);
+}
+
+int rb_c51_dueling_loss_grad(const rb_head_params* online, const float* part2_online, const rb_head_params* target,
+                             const float* part2_target, const int64_t* actions, const float* returns,
+                             const float* nonterminals, const float* weights, const float* support, float vmin, float vmax,
+                             float delta_z, float gamma_n, int B, float* loss, float* dz, float* m_out, int64_t* astar_out,
+                             rb_stream_t stream) {
+  if (!online || !target || !part2_online || !part2_target || !actions || !returns || !nonterminals || !weights || !support ||
+      !loss || !dz)
+    return fail(RB_ERR_INVAL, "rb_c51_dueling_loss_grad: null pointer");
+  const int Z = online->atoms, A = online->actions;
+  if (B <= 0 || A <= 0 || Z <= 1 || target->atoms != Z || target->actions != A || target->hidden != online->hidden ||
+      target->conv_features != online->conv_features)
+    return fail(RB_ERR_INVAL, "rb_c51_dueling_loss_grad: inconsistent sizes");
+  if (Z > RB_MAX_ATOMS) return fail(RB_ERR_RANGE, "rb_c51_dueling_loss_grad: Z exceeds RB_MAX_ATOMS");
+  int s1 = 0, s2 = 0;
+  int rc = rb_head_splits(online->conv_features, online->hidden, &s1, &s2);
+  if (rc != RB_OK) return rc;
+  DuelSide on, tg;
+  for (int s = 0; s < 2; ++s) {
+    on.b2_mu[s] = online->b2_mu[s]; on.b2_sig[s] = online->b2_sigma[s]; on.eo2[s] = online->eps_out2[s];
+    tg.b2_mu[s] = target->b2_mu[s]; tg.b2_sig[s] = target->b2_sigma[s]; tg.eo2[s] = target->eps_out2[s];
+    if (!on.b2_mu[s] || !on.b2_sig[s] || !tg.b2_mu[s] || !tg.b2_sig[s]) return fail(RB_ERR_INVAL, "rb_c51_dueling_loss_grad: null bias pointer");
+  }
+  on.part2 = part2_online; on.s2 = s2; on.rows = 2 * B;
+  tg.part2 = part2_target; tg.s2 = s2; tg.rows = B;
+  const size_t smem = (size_t)C51_WARPS * (2 * A * Z + Z) * sizeof(float);
+  if (smem > 160 * 1024) return fail(RB_ERR_RANGE, "rb_c51_dueling_loss_grad: actions * atoms too large");
+  if (smem > 40 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_c51_dueling, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(RB_ERR_CUDA, cudaGetErrorString(e));
+  }
+  const int ctas = (B + C51_WARPS - 1) / C51_WARPS;
+  { ProfScope prof_(RB_K_C51_DUELING, (cudaStream_t)stream);
+    k_c51_dueling<<<ctas, C51_WARPS * 32, smem, (cudaStream_t)stream>>>(on, tg, actions, returns, nonterminals, weights, support,
+                                                                      vmin, vmax, delta_z, gamma_n, B, A, Z, loss, dz, m_out,
+                                                                      astar_out); }
+  return check_launch("rb_c51_dueling_loss_grad");
 }
 
 int rb_noisy_compose(const float* mu, const float* sigma, const float* eps, int64_t count, float* out, rb_stream_t stream) {

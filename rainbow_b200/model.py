@@ -4,12 +4,18 @@ API and state_dict layout follow the reference's model.py (NoisyLinear model.py:
 model.py:49-85) so checkpoints interchange: convs.{0,2,4}.{weight,bias} and
 fc_{h_v,h_a,z_v,z_a}.{weight_mu,weight_sigma,bias_mu,bias_sigma,weight_epsilon,bias_epsilon}.
 
-Per the north star the conv/GEMM body stays a cuDNN/cuBLAS torch forward.  What is ours:
-  * reset_noise(): all four NoisyLinear layers of a net are resampled by ONE rb_noisy_resample launch
-    (device Philox + Box-Muller, f(x)=sign(x)sqrt|x|, outer product streamed straight into the
-    weight_epsilon buffers) instead of the reference's ~52 ATen ops (model.py:32-40, 82-85);
-  * logits(): the pre-softmax dueling combination (model.py:75), which the fused C51 kernel consumes
-    (the softmax / log_softmax of model.py:76-79 are folded into that kernel).
+Per the north star the conv body stays a cuDNN torch forward.  What is ours:
+  * noise lives as FACTOR VECTORS f(eps_in), f(eps_out) per layer (model.py:36-38); reset_noise() is one tiny
+    rb_noise_factors launch (device Philox + Box-Muller) instead of the reference's ~52 ATen ops and 13.6 MB of
+    weight_epsilon writes per net.  The weight_epsilon / bias_epsilon buffers of the state_dict are materialised
+    lazily (rb_noisy_outer) only when somebody looks at them (state_dict(), the library-GEMM fallback path);
+  * the noisy dueling head (model.py:69-75 after the convs) runs through the fused head kernels
+    (rb_head_forward / rb_head_logits, csrc/rb_head.cu), which compose W = mu + sigma*eps on the fly;
+  * logits(): the pre-softmax dueling combination (model.py:75), which the fused C51 kernel consumes.
+
+Autograd: when gradients are being recorded (an external caller training through forward()), logits() uses the
+plain torch path (composed weights + F.linear) so autograd works as in the reference; the learner in
+rainbow_b200.agent drives the fused forward AND backward kernels itself.
 """
 import ctypes as C
 import math
@@ -46,12 +52,12 @@ class NoisyLinear(nn.Module):
         """Construction-time only (host, before the module is moved to the GPU): the reference draws one
         noise sample in __init__ (model.py:23).  Doing the same keeps the torch RNG stream -- and therefore
         every later layer's initial weights -- identical to the reference for the same seed.  The learner
-        never uses this path: DQN.reset_noise() is the CUDA kernel."""
+        never uses this path: DQN.reset_noise() is a CUDA kernel."""
         with torch.no_grad():
             x_in, x_out = torch.randn(self.in_features), torch.randn(self.out_features)
-            f_in, f_out = x_in.sign() * x_in.abs().sqrt(), x_out.sign() * x_out.abs().sqrt()
-            self.weight_epsilon.copy_(torch.outer(f_out, f_in))
-            self.bias_epsilon.copy_(f_out)
+            self._f_in, self._f_out = x_in.sign() * x_in.abs().sqrt(), x_out.sign() * x_out.abs().sqrt()
+            self.weight_epsilon.copy_(torch.outer(self._f_out, self._f_in))
+            self.bias_epsilon.copy_(self._f_out)
 
     def reset_parameters(self):  # model.py:25-30
         bound = 1.0 / math.sqrt(self.in_features)
@@ -69,17 +75,97 @@ class NoisyLinear(nn.Module):
         return F.linear(x, self.weight_mu, self.bias_mu)
 
 
-def resample_noise(layers, seed, rng_counter, x_in=None, x_out=None):
-    """One rb_noisy_resample launch over `layers` (NoisyLinear modules on one CUDA device).
-    x_in / x_out: optional injected raw normals (parity mode), concatenated over layers."""
-    lib = _lib.load()
+def _layer_arrays(layers):
     n = len(layers)
-    w = (C.c_void_p * n)(*[_lib.ptr(m.weight_epsilon) for m in layers])
-    b = (C.c_void_p * n)(*[_lib.ptr(m.bias_epsilon) for m in layers])
-    fin = (C.c_int * n)(*[m.in_features for m in layers])
-    fout = (C.c_int * n)(*[m.out_features for m in layers])
-    _lib.check(lib.rb_noisy_resample(w, b, fin, fout, n, _lib.ptr(x_in), _lib.ptr(x_out), seed,
-                                     _lib.ptr(rng_counter), _lib.stream()))
+    return ((C.c_void_p * n)(*[_lib.ptr(m.weight_epsilon) for m in layers]),
+            (C.c_void_p * n)(*[_lib.ptr(m.bias_epsilon) for m in layers]),
+            (C.c_int * n)(*[m.in_features for m in layers]), (C.c_int * n)(*[m.out_features for m in layers]), n)
+
+
+def resample_noise(layers, seed, rng_counter, x_in=None, x_out=None):
+    """One rb_noisy_resample launch (K6) over `layers`: draws AND materialises weight_epsilon / bias_epsilon.
+    x_in / x_out: optional injected raw normals (parity mode), concatenated over layers."""
+    w, b, fin, fout, n = _layer_arrays(layers)
+    _lib.check(_lib.load().rb_noisy_resample(w, b, fin, fout, n, _lib.ptr(x_in), _lib.ptr(x_out), seed,
+                                             _lib.ptr(rng_counter), _lib.stream()))
+
+
+class FusedHead:
+    """Launcher of the fused noisy dueling head kernels for one DQN (csrc/rb_head.cu)."""
+
+    MAX_ROWS = 4096
+
+    def __init__(self, net):
+        self.net = net
+        self.lib = _lib.load()
+        s1, s2 = C.c_int(), C.c_int()
+        _lib.check(self.lib.rb_head_splits(net.conv_output_size, net.hidden_size, C.byref(s1), C.byref(s2)))
+        self.s1, self.s2 = s1.value, s2.value
+        self.ncols = net.atoms * (1 + net.action_space)
+        self._scratch = {}
+
+    @staticmethod
+    def supported(net):
+        return (net.conv_output_size % 32 == 0 and net.hidden_size % 64 == 0 and net.atoms <= 128 and
+                next(net.parameters()).is_cuda)
+
+    def params(self, noisy=None):
+        net = self.net
+        noisy = net.training if noisy is None else noisy
+        p = _lib.HeadParams()
+        (hv, ha), (zv, za) = (net.fc_h_v, net.fc_h_a), (net.fc_z_v, net.fc_z_a)
+        for s, (l1, l2) in enumerate(((hv, zv), (ha, za))):
+            p.w1_mu[s], p.w1_sigma[s] = _lib.ptr(l1.weight_mu), _lib.ptr(l1.weight_sigma)
+            p.b1_mu[s], p.b1_sigma[s] = _lib.ptr(l1.bias_mu), _lib.ptr(l1.bias_sigma)
+            p.w2_mu[s], p.w2_sigma[s] = _lib.ptr(l2.weight_mu), _lib.ptr(l2.weight_sigma)
+            p.b2_mu[s], p.b2_sigma[s] = _lib.ptr(l2.bias_mu), _lib.ptr(l2.bias_sigma)
+        if noisy:
+            f = net.noise_factors()  # {layer name: (f_in, f_out)}
+            for s, (n1, n2) in enumerate((("fc_h_v", "fc_z_v"), ("fc_h_a", "fc_z_a"))):
+                p.eps_in1[s], p.eps_out1[s] = _lib.ptr(f[n1][0]), _lib.ptr(f[n1][1])
+                p.eps_in2[s], p.eps_out2[s] = _lib.ptr(f[n2][0]), _lib.ptr(f[n2][1])
+        p.conv_features, p.hidden, p.atoms, p.actions = net.conv_output_size, net.hidden_size, net.atoms, net.action_space
+        return p
+
+    def grads(self):
+        """rb_head_grads pointing at the .grad storage of the 16 head parameters (must exist)."""
+        net = self.net
+        g = _lib.HeadGrads()
+        for s, (l1, l2) in enumerate(((net.fc_h_v, net.fc_z_v), (net.fc_h_a, net.fc_z_a))):
+            g.w1_mu[s], g.w1_sigma[s] = _lib.ptr(l1.weight_mu.grad), _lib.ptr(l1.weight_sigma.grad)
+            g.b1_mu[s], g.b1_sigma[s] = _lib.ptr(l1.bias_mu.grad), _lib.ptr(l1.bias_sigma.grad)
+            g.w2_mu[s], g.w2_sigma[s] = _lib.ptr(l2.weight_mu.grad), _lib.ptr(l2.weight_sigma.grad)
+            g.b2_mu[s], g.b2_sigma[s] = _lib.ptr(l2.bias_mu.grad), _lib.ptr(l2.bias_sigma.grad)
+        return g
+
+    def _buffers(self, M, dev):
+        if M not in self._scratch:
+            H = self.net.hidden_size
+            self._scratch[M] = (torch.empty((self.s1, M, 2 * H), dtype=torch.float32, device=dev),
+                                torch.empty((M, 2 * H), dtype=torch.float32, device=dev),
+                                torch.empty((self.s2, M, self.ncols), dtype=torch.float32, device=dev))
+        return self._scratch[M]
+
+    def forward(self, x_lo, x_hi=None, noisy=None):
+        """x_lo [m_lo, K1] (+ x_hi [m_hi, K1]) -> (part2 [s2, M, Z(1+A)], h [M, 2H]); buffers are reused per M."""
+        m_lo = x_lo.shape[0]
+        m_hi = 0 if x_hi is None else x_hi.shape[0]
+        part1, h, part2 = self._buffers(m_lo + m_hi, x_lo.device)
+        p = self.params(noisy)
+        _lib.check(self.lib.rb_head_forward(C.byref(p), _lib.ptr(x_lo), m_lo, _lib.ptr(x_hi), m_hi, _lib.ptr(part1),
+                                            _lib.ptr(h), _lib.ptr(part2), _lib.stream()))
+        return part2, h, p
+
+    def logits(self, part2, p, M):
+        q = torch.empty((M, self.net.action_space, self.net.atoms), dtype=torch.float32, device=part2.device)
+        _lib.check(self.lib.rb_head_logits(C.byref(p), _lib.ptr(part2), M, _lib.ptr(q), _lib.stream()))
+        return q
+
+    def backward(self, p, x, h, dz, dh_scratch, dx):
+        g = self.grads()
+        _lib.check(self.lib.rb_head_backward(C.byref(p), C.byref(g), _lib.ptr(x), _lib.ptr(h), _lib.ptr(dz), x.shape[0],
+                                             _lib.ptr(dh_scratch), _lib.ptr(dx), _lib.stream()))
+        return dx
 
 
 class DQN(nn.Module):
@@ -87,6 +173,7 @@ class DQN(nn.Module):
         super().__init__()
         self.atoms = args.atoms
         self.action_space = action_space
+        self.hidden_size = args.hidden_size
         if args.architecture not in _ARCH:
             raise ValueError(f"unknown architecture '{args.architecture}'")
         specs, self.conv_output_size = _ARCH[args.architecture]
@@ -101,25 +188,94 @@ class DQN(nn.Module):
         self.fc_z_a = NoisyLinear(args.hidden_size, action_space * self.atoms, std_init=args.noisy_std)
         self.noise_seed = int(torch.initial_seed()) & (2 ** 63 - 1)
         self.register_buffer("_noise_counter", torch.zeros(1, dtype=torch.int64), persistent=False)
+        # factor vectors of all layers back to back, in reset order: f(eps_in) | f(eps_out)
+        layers = self.noisy_layers()
+        self.register_buffer("_f_in", torch.cat([m._f_in for m in layers]), persistent=False)
+        self.register_buffer("_f_out", torch.cat([m._f_out for m in layers]), persistent=False)
+        self._eps_stale = False  # weight_epsilon / bias_epsilon buffers currently equal the outer product of the factors
+        self._head = None
+        self.use_fused_head = True
 
+    # ---- noise ---------------------------------------------------------------------------------------
     def noisy_layers(self):
         """Layers in the reference's reset order (named_children containing 'fc', model.py:83-85)."""
         return [m for name, m in self.named_children() if "fc" in name]
 
+    def noise_factors(self):
+        out, oi, oo = {}, 0, 0
+        for name, m in self.named_children():
+            if "fc" in name:
+                out[name] = (self._f_in[oi:oi + m.in_features], self._f_out[oo:oo + m.out_features])
+                oi, oo = oi + m.in_features, oo + m.out_features
+        return out
+
+    def reset_noise(self, x_in=None, x_out=None):
+        """model.py:82-85: new factor vectors for every NoisyLinear, one launch.  x_in / x_out: optional injected
+        raw normals (parity).  Needs the network on a CUDA device."""
+        if not self._f_in.is_cuda:
+            raise _lib.RainbowB200Error("DQN.reset_noise needs the network on a CUDA device (no CPU fallback)")
+        _lib.check(_lib.load().rb_noise_factors(_lib.ptr(self._f_in), self._f_in.numel(), _lib.ptr(self._f_out),
+                                                self._f_out.numel(), _lib.ptr(x_in), _lib.ptr(x_out), self.noise_seed,
+                                                _lib.ptr(self._noise_counter), _lib.stream()))
+        self._eps_stale = True
+
+    def materialise_noise(self):
+        """Bring weight_epsilon / bias_epsilon (model.py:39-40) up to date with the factor vectors."""
+        if self._eps_stale:
+            w, b, fin, fout, n = _layer_arrays(self.noisy_layers())
+            _lib.check(_lib.load().rb_noisy_outer(w, b, fin, fout, n, _lib.ptr(self._f_in), _lib.ptr(self._f_out),
+                                                  _lib.stream()))
+            self._eps_stale = False
+
+    def _factors_from_buffers(self):
+        """After load_state_dict: recover the rank-one factors from the loaded epsilon buffers
+        (eps_out = bias_epsilon; eps_in = the weight_epsilon row of the largest |eps_out| divided by it)."""
+        with torch.no_grad():
+            fi, fo = [], []
+            for m in self.noisy_layers():
+                b = m.bias_epsilon
+                o = int(b.abs().argmax())
+                fo.append(b.clone())
+                fi.append(m.weight_epsilon[o] / b[o] if float(b[o]) != 0.0 else torch.zeros_like(m.weight_epsilon[0]))
+            self._f_in.copy_(torch.cat(fi))
+            self._f_out.copy_(torch.cat(fo))
+        self._eps_stale = False
+
+    def state_dict(self, *args, **kwargs):
+        if self._eps_stale and self._f_in.is_cuda:
+            self.materialise_noise()
+        return super().state_dict(*args, **kwargs)
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        out = super().load_state_dict(state_dict, *args, **kwargs)
+        self._factors_from_buffers()
+        return out
+
+    # ---- forward -------------------------------------------------------------------------------------
+    def head(self):
+        if self._head is None:
+            self._head = FusedHead(self)
+        return self._head
+
+    def fused_ok(self, rows):
+        return self.use_fused_head and rows <= FusedHead.MAX_ROWS and FusedHead.supported(self)
+
+    def features(self, x):
+        return self.convs(x).view(-1, self.conv_output_size)
+
     def logits(self, x):
         """Pre-softmax q [B, A, Z] (model.py:69-75)."""
-        x = self.convs(x).view(-1, self.conv_output_size)
-        v = self.fc_z_v(F.relu(self.fc_h_v(x))).view(-1, 1, self.atoms)
-        a = self.fc_z_a(F.relu(self.fc_h_a(x))).view(-1, self.action_space, self.atoms)
+        feats = self.features(x)
+        recording = torch.is_grad_enabled() and (feats.requires_grad or self.fc_h_v.weight_mu.requires_grad)
+        if not recording and self.fused_ok(feats.shape[0]):
+            part2, _, p = self.head().forward(feats.contiguous())
+            return self.head().logits(part2, p, feats.shape[0])
+        if self._eps_stale:
+            self.materialise_noise()
+        v = self.fc_z_v(F.relu(self.fc_h_v(feats))).view(-1, 1, self.atoms)
+        a = self.fc_z_a(F.relu(self.fc_h_a(feats))).view(-1, self.action_space, self.atoms)
         return v + a - a.mean(1, keepdim=True)
 
     def forward(self, x, log=False):
         q = self.logits(x)
         return F.log_softmax(q, dim=2) if log else F.softmax(q, dim=2)
-
-    def reset_noise(self, x_in=None, x_out=None):
-        """model.py:82-85: one kernel launch for all layers.  Needs the network on a CUDA device."""
-        layers = self.noisy_layers()
-        if not layers[0].weight_epsilon.is_cuda:
-            raise _lib.RainbowB200Error("DQN.reset_noise needs the network on a CUDA device (no CPU fallback)")
-        resample_noise(layers, self.noise_seed, self._noise_counter, x_in, x_out)

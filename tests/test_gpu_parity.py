@@ -435,7 +435,8 @@ class FakeEnv:
         return self.a
 
 
-def test_learner_step_vs_reference_golden():
+@pytest.mark.parametrize("fused", [True, False], ids=["fused_head", "library_gemm_head"])
+def test_learner_step_vs_reference_golden(fused):
     """End to end: one Agent.learn on a tiny data-efficient net vs the unmodified reference CPU run
     (tests/golden/model_step.npz): same initial weights, same batch, same target-net noise draw.
     GPU conv/GEMM (fp32, TF32 off) vs CPU conv/GEMM: loss within 1e-5, gradients within 1e-6 abs."""
@@ -444,7 +445,7 @@ def test_learner_step_vs_reference_golden():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     B, A = 4, 3
-    args = make_args(batch_size=B, architecture="data-efficient", hidden_size=32, multi_step=3, cuda_graph=False)
+    args = make_args(batch_size=B, architecture="data-efficient", hidden_size=64, multi_step=3, cuda_graph=False, fused_head=fused)
     ag = Agent(args, FakeEnv(A))
     sd0 = {k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd0.")}
     ag.online_net.load_state_dict(sd0)
@@ -457,6 +458,7 @@ def test_learner_step_vs_reference_golden():
     # target noise: randn order is eps_in, eps_out per layer (model.py:37-38), layers in reset order
     x_in = t(np.concatenate([g[f"target_randn{2 * i}"] for i in range(4)]))
     x_out = t(np.concatenate([g[f"target_randn{2 * i + 1}"] for i in range(4)]))
+    assert ag._fused_path(B) == fused
     loss = ag._update_from_batch(batch, target_noise=(x_in, x_out))
     np.testing.assert_allclose(cpu(loss), g["loss"], rtol=1e-5, atol=1e-5)
     for k, p in ag.online_net.named_parameters():
@@ -470,6 +472,137 @@ def test_learner_step_vs_reference_golden():
     lr = args.learning_rate
     for k, p in ag.online_net.named_parameters():
         np.testing.assert_allclose(cpu(p), g["sd1." + k], rtol=0, atol=0.02 * lr, err_msg=k)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused noisy dueling head (csrc/rb_head.cu) against the library path (composed weights + F.linear + autograd)
+def _head_net(arch="canonical", hidden=512, actions=6, seed=0):
+    from rainbow_b200.model import DQN
+    torch.manual_seed(seed)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = DQN(make_args(architecture=arch, hidden_size=hidden), actions).to(DEV)
+    with torch.no_grad():  # make sigma non-trivial so the noise terms matter
+        for m in net.noisy_layers():
+            m.weight_sigma.mul_(torch.empty_like(m.weight_sigma).uniform_(0.5, 3.0))
+            m.bias_sigma.mul_(torch.empty_like(m.bias_sigma).uniform_(0.5, 3.0))
+    net.reset_noise()
+    return net
+
+
+def _library_head(net, feats):
+    """Reference formulation on the GPU: materialised weight_epsilon, composed weights, F.linear (model.py:42-44,73-75)."""
+    import torch.nn.functional as F
+    net.materialise_noise()
+    v = net.fc_z_v(F.relu(net.fc_h_v(feats)))
+    a = net.fc_z_a(F.relu(net.fc_h_a(feats)))
+    return v, a
+
+
+@pytest.mark.parametrize("arch,hidden,actions", [("canonical", 512, 6), ("data-efficient", 256, 18), ("data-efficient", 64, 3)])
+@pytest.mark.parametrize("rows", [1, 32, 64, 100])
+def test_fused_head_forward(arch, hidden, actions, rows):
+    net = _head_net(arch, hidden, actions)
+    feats = torch.randn(rows, net.conv_output_size, device=DEV).relu()
+    with torch.no_grad():
+        for mode in ("train", "eval"):
+            getattr(net, mode)()
+            v, a = _library_head(net, feats)
+            q_ref = v.view(rows, 1, -1) + a.view(rows, actions, -1) - a.view(rows, actions, -1).mean(1, keepdim=True)
+            part2, h, p = net.head().forward(feats[:rows // 2 + 1].contiguous(), feats[rows // 2 + 1:].contiguous() if rows > 1 else None)
+            q = net.head().logits(part2, p, rows)
+            np.testing.assert_allclose(cpu(q), cpu(q_ref), rtol=1e-4, atol=2e-5)
+            import torch.nn.functional as F
+            h_ref = torch.cat([F.relu(net.fc_h_v(feats)), F.relu(net.fc_h_a(feats))], 1)
+            np.testing.assert_allclose(cpu(h), cpu(h_ref), rtol=1e-4, atol=2e-5)
+    net.train()
+    x = torch.rand(3, 4, 84, 84, device=DEV)
+    with torch.no_grad():
+        q_f = net.logits(x)                       # fused inference path (what Agent.act uses)
+        net.use_fused_head = False
+        q_l = net.logits(x)
+    np.testing.assert_allclose(cpu(q_f), cpu(q_l), rtol=1e-4, atol=2e-5)
+
+
+def test_noise_factors_plus_outer_equals_resample():
+    from rainbow_b200.model import resample_noise
+    net = _head_net()
+    ctr0 = int(net._noise_counter.item())
+    net.materialise_noise()
+    w_fact = [cpu(m.weight_epsilon).copy() for m in net.noisy_layers()]
+    b_fact = [cpu(m.bias_epsilon).copy() for m in net.noisy_layers()]
+    ctr = torch.tensor([ctr0 - 1], dtype=torch.int64, device=DEV)     # the draw reset_noise() consumed
+    resample_noise(net.noisy_layers(), net.noise_seed, ctr)            # K6 with the same seed / counter
+    for m, w, b in zip(net.noisy_layers(), w_fact, b_fact):
+        assert_bits_equal(cpu(m.weight_epsilon), w, "weight_epsilon")
+        assert_bits_equal(cpu(m.bias_epsilon), b, "bias_epsilon")
+    # state_dict() materialises, load_state_dict() recovers the factors (to rounding)
+    net.reset_noise()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    f_in, f_out = net._f_in.clone(), net._f_out.clone()
+    net.reset_noise()
+    net.load_state_dict(sd)
+    np.testing.assert_allclose(cpu(net._f_out), cpu(f_out), rtol=0, atol=0)
+    np.testing.assert_allclose(cpu(net._f_in), cpu(f_in), rtol=3e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("arch,hidden,actions,B", [("canonical", 512, 6, 32), ("data-efficient", 256, 4, 17), ("data-efficient", 64, 3, 1)])
+def test_fused_head_backward(arch, hidden, actions, B):
+    net = _head_net(arch, hidden, actions, seed=1)
+    K1, Z = net.conv_output_size, net.atoms
+    feats = torch.randn(B, K1, device=DEV).relu().requires_grad_(True)
+    dz = torch.randn(B, Z * (1 + actions), device=DEV) * 0.1
+    v, a = _library_head(net, feats)
+    out = torch.cat([v, a], 1)
+    params = [p for m in net.noisy_layers() for p in (m.weight_mu, m.weight_sigma, m.bias_mu, m.bias_sigma)]
+    ref = torch.autograd.grad(out, [feats] + params, dz)
+    for p in params:
+        p.grad = torch.full_like(p, 123.0)       # must be overwritten, not accumulated
+    with torch.no_grad():
+        part2, h, p_ = net.head().forward(feats.detach())
+        dh = torch.empty(B, 2 * hidden, device=DEV)
+        dx = torch.empty(B, K1, device=DEV)
+        net.head().backward(p_, feats.detach(), h[:B], dz, dh, dx)
+    scale = lambda t: float(t.abs().max()) + 1e-12
+    np.testing.assert_allclose(cpu(dx), cpu(ref[0]), rtol=0, atol=2e-5 * scale(ref[0]))
+    for p, r in zip(params, ref[1:]):
+        np.testing.assert_allclose(cpu(p.grad), cpu(r), rtol=0, atol=2e-5 * scale(r))
+
+
+@pytest.mark.parametrize("actions,B", [(6, 32), (18, 5)])
+def test_c51_dueling_entry(actions, B):
+    """rb_c51_dueling_loss_grad (fed by head partials) == rb_c51_loss_grad on the assembled logits, and its dz is
+    the dueling-combine backward of the logit gradient."""
+    from rainbow_b200.agent import c51_dueling_loss_grad, c51_loss_grad
+    on, tg = _head_net("data-efficient", 128, actions, seed=2), _head_net("data-efficient", 128, actions, seed=3)
+    K1, Z, A = on.conv_output_size, on.atoms, actions
+    rs = np.random.RandomState(0)
+    x = torch.randn(2 * B, K1, device=DEV).relu() * 3
+    t = lambda a: torch.from_numpy(a).to(DEV)
+    acts = t(rs.randint(0, A, B).astype(np.int64))
+    rets = t(rs.uniform(-2, 2, B).astype(np.float32))
+    nont = t((rs.uniform(size=(B, 1)) > 0.2).astype(np.float32))
+    w = t(rs.uniform(0.2, 1, B).astype(np.float32))
+    support = torch.linspace(-10, 10, Z).to(DEV)
+    with torch.no_grad():
+        p2_on, _, p_on = on.head().forward(x[:B].contiguous(), x[B:].contiguous())
+        p2_on = p2_on.clone()
+        p2_t, _, p_t = tg.head().forward(x[B:].contiguous())
+        q_on = on.head().logits(p2_on, p_on, 2 * B)
+        q_t = tg.head().logits(p2_t, p_t, B)
+        m1 = torch.empty(B, Z, device=DEV); m2 = torch.empty(B, Z, device=DEV)
+        a1 = torch.empty(B, dtype=torch.int64, device=DEV); a2 = torch.empty(B, dtype=torch.int64, device=DEV)
+        loss_ref, gq = c51_loss_grad(q_on[:B].contiguous(), q_on[B:].contiguous(), q_t, acts, rets, nont, w, support, -10.0, 10.0,
+                                     0.4, 0.99 ** 3, m_out=m1, astar_out=a1)
+        loss, dz = c51_dueling_loss_grad(p_on, p2_on, p_t, p2_t, acts, rets, nont, w, support, -10.0, 10.0, 0.4, 0.99 ** 3,
+                                         m_out=m2, astar_out=a2)
+    assert torch.equal(a1, a2)
+    np.testing.assert_allclose(cpu(m2), cpu(m1), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(cpu(loss), cpu(loss_ref), rtol=1e-5, atol=1e-5)
+    dzv_ref = gq.sum(1)                                            # q = zv + za - mean_a za
+    dza_ref = gq - gq.mean(1, keepdim=True)
+    np.testing.assert_allclose(cpu(dz[:, :Z]), cpu(dzv_ref), rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(cpu(dz[:, Z:]).reshape(B, A, Z), cpu(dza_ref), rtol=1e-5, atol=1e-8)
 
 
 def test_agent_learn_graph_and_eager():
