@@ -379,8 +379,9 @@ def test_noise_philox_statistics():
     from rainbow_b200.model import DQN
     net = DQN(make_args(), 6).to(DEV)
     net.reset_noise()
-    w1 = cpu(net.fc_h_v.weight_epsilon).copy()
-    b1 = cpu(net.fc_h_v.bias_epsilon).copy()
+    sd = net.state_dict()                     # weight_epsilon / bias_epsilon are materialised lazily, on inspection
+    w1 = cpu(sd["fc_h_v.weight_epsilon"]).copy()
+    b1 = cpu(sd["fc_h_v.bias_epsilon"]).copy()
     # rank 1: W[o, i] == b[o] * e_in[i] with e_in recovered from one row
     o0 = int(np.argmax(np.abs(b1)))
     e_in = w1[o0] / b1[o0]
@@ -393,7 +394,7 @@ def test_noise_philox_statistics():
     x = np.sign(allv) * allv ** 2  # invert f: should be standard normal
     assert abs(np.std(x) - 1.0) < 0.05 and abs(np.mean(x ** 4) - 3.0) < 0.5
     net.reset_noise()
-    assert not np.array_equal(cpu(net.fc_h_v.weight_epsilon), w1)
+    assert not np.array_equal(cpu(net.state_dict()["fc_h_v.weight_epsilon"]), w1)
     assert int(net._noise_counter.item()) == 2
     # layers do not share draws
     assert not np.array_equal(cpu(net.fc_h_a.bias_epsilon), cpu(net.fc_h_v.bias_epsilon))
