@@ -183,30 +183,33 @@ typedef struct rb_head_grads {   /* gradients are OVERWRITTEN (not accumulated) 
   float* w2_mu[2]; float* w2_sigma[2]; float* b2_mu[2]; float* b2_sigma[2];
 } rb_head_grads;
 
-/* split-K factors used by the head kernels: part1 is float32[s1][M][2*hidden], part2 float32[s2][M][atoms*(1+actions)] */
+/* split-K factors used by the head kernels: scratch part1 is float32[s1][M][2*hidden], part2 float32[s2][M][atoms*(1+actions)];
+ * tickets is int32[rb_head_ticket_count()], zero-initialised ONCE by the caller (the kernels leave it zeroed). */
 int rb_head_splits(int conv_features, int hidden, int* s1, int* s2);
+int rb_head_ticket_count(void);
 
 /* Forward over M = m_lo + m_hi rows (x_lo: [m_lo][conv_features], x_hi: [m_hi][conv_features] or NULL).
- * Writes the split-K partials part1, part2 and (if h != NULL) the hidden activations h[M][2*hidden]
- * (value stream in columns [0,hidden), advantage stream in [hidden, 2*hidden)). */
-int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const float* x_hi, int m_hi, float* part1, float* h,
-                    float* part2, rb_stream_t stream);
+ * Outputs: h[M][2*hidden] (post-ReLU hidden activations, value stream in columns [0,hidden), advantage stream in
+ * [hidden,2*hidden)) and z[M][atoms*(1+actions)] = (z_value | z_advantage), biases included.  Two launches; the
+ * split-K partials are reduced inside the kernels (last-arriving CTA, fixed order: deterministic). */
+int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const float* x_hi, int m_hi, float* part1, float* part2,
+                    int32_t* tickets, float* h, float* z, rb_stream_t stream);
 
-/* q[M][actions][atoms] = zv + za - mean_a(za) (model.py:75) from part2 (+ composed layer-2 bias). */
-int rb_head_logits(const rb_head_params* p, const float* part2, int M, float* q, rb_stream_t stream);
+/* q[M][actions][atoms] = zv + za - mean_a(za) (model.py:75) from z. */
+int rb_head_logits(const float* z, int M, int actions, int atoms, float* q, rb_stream_t stream);
 
 /* Backward for B <= 32 rows: given dz[B][atoms*(1+actions)] (value block first), x[B][conv_features] and h[B][2*hidden]
  * writes all 16 parameter gradients through `g` and dx[B][conv_features].  dh_scratch: float32[B][2*hidden]. */
 int rb_head_backward(const rb_head_params* p, const rb_head_grads* g, const float* x, const float* h, const float* dz, int B,
                      float* dh_scratch, float* dx, rb_stream_t stream);
 
-/* rb_c51_loss_grad fed by the fused heads: online part2 has 2B rows (s then s'), target part2 B rows (s');
- * returns loss[B] and dz[B][atoms*(1+actions)] = d mean(w*loss) / d (z_value | z_advantage) of the online(s) rows. */
-int rb_c51_dueling_loss_grad(const rb_head_params* online, const float* part2_online, const rb_head_params* target,
-                             const float* part2_target, const int64_t* actions, const float* returns,
-                             const float* nonterminals, const float* weights, const float* support, float vmin, float vmax,
-                             float delta_z, float gamma_n, int B, float* loss, float* dz, float* m_out, int64_t* astar_out,
-                             rb_stream_t stream);
+/* rb_c51_loss_grad fed by the fused heads: z_online has 2B rows (s then s'), z_target B rows (s');
+ * returns loss[B] and dz[B][atoms*(1+actions)] = d mean(w*loss) / d (z_value | z_advantage) of the online(s) rows
+ * (the dueling combination model.py:75 and its backward are folded in). */
+int rb_c51_dueling_loss_grad(const float* z_online, const float* z_target, int actions_n, int atoms, const int64_t* actions,
+                             const float* returns, const float* nonterminals, const float* weights, const float* support,
+                             float vmin, float vmax, float delta_z, float gamma_n, int B, float* loss, float* dz, float* m_out,
+                             int64_t* astar_out, rb_stream_t stream);
 
 /* model.py:43-44 NoisyLinear.forward weight composition W = mu + sigma*eps (elementwise),
  * used for both weights ([out*in]) and biases ([out]). */

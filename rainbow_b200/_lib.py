@@ -45,10 +45,11 @@ SIGNATURES = {
     "rb_noisy_outer": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "rb_noise_factors": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _u64, _vp, _vp]),
     "rb_head_splits": (C.c_int, [_i32, _i32, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
-    "rb_head_forward": (C.c_int, [_hp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
-    "rb_head_logits": (C.c_int, [_hp, _vp, _i32, _vp, _vp]),
+    "rb_head_ticket_count": (C.c_int, []),
+    "rb_head_forward": (C.c_int, [_hp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rb_head_logits": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "rb_head_backward": (C.c_int, [_hp, _hg, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
-    "rb_c51_dueling_loss_grad": (C.c_int, [_hp, _vp, _hp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32,
+    "rb_c51_dueling_loss_grad": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32,
                                            _vp, _vp, _vp, _vp, _vp]),
     "rb_noisy_compose": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "rb_clip_adam_scratch_elems": (C.c_int, []),

@@ -43,20 +43,17 @@ def c51_loss_grad(q_online_s, q_online_ns, q_target_ns, actions, returns, nonter
     return loss, grad
 
 
-def c51_dueling_loss_grad(p_online, part2_online, p_target, part2_target, actions, returns, nonterminals, weights, support,
-                          vmin, vmax, delta_z, gamma_n, m_out=None, astar_out=None):
-    """K3 fed straight by the fused heads' split-K partials (rb_c51_dueling_loss_grad): returns (loss[B],
-    dz[B, Z(1+A)]) with dz = d mean(w*loss) / d (z_value | z_advantage) of the online(s) rows."""
-    import ctypes as C
+def c51_dueling_loss_grad(z_online, z_target, actions_n, atoms, actions, returns, nonterminals, weights, support, vmin, vmax,
+                          delta_z, gamma_n, m_out=None, astar_out=None):
+    """K3 fed straight by the fused heads (rb_c51_dueling_loss_grad): z_online [2B, Z(1+A)] (s rows, then s' rows),
+    z_target [B, Z(1+A)]; returns (loss[B], dz[B, Z(1+A)]) with dz = d mean(w*loss) / d (z_value | z_advantage)."""
     B = actions.shape[0]
-    ncols = p_online.atoms * (1 + p_online.actions)
     loss = torch.empty(B, dtype=torch.float32, device=actions.device)
-    dz = torch.empty((B, ncols), dtype=torch.float32, device=actions.device)
+    dz = torch.empty((B, atoms * (1 + actions_n)), dtype=torch.float32, device=actions.device)
     _lib.check(_lib.load().rb_c51_dueling_loss_grad(
-        C.byref(p_online), _lib.ptr(part2_online), C.byref(p_target), _lib.ptr(part2_target), _lib.ptr(actions),
-        _lib.ptr(returns), _lib.ptr(nonterminals), _lib.ptr(weights), _lib.ptr(support), float(vmin), float(vmax),
-        float(delta_z), float(gamma_n), B, _lib.ptr(loss), _lib.ptr(dz), _lib.ptr(m_out), _lib.ptr(astar_out),
-        _lib.stream()))
+        _lib.ptr(z_online), _lib.ptr(z_target), actions_n, atoms, _lib.ptr(actions), _lib.ptr(returns),
+        _lib.ptr(nonterminals), _lib.ptr(weights), _lib.ptr(support), float(vmin), float(vmax), float(delta_z),
+        float(gamma_n), B, _lib.ptr(loss), _lib.ptr(dz), _lib.ptr(m_out), _lib.ptr(astar_out), _lib.stream()))
     return loss, dz
 
 
@@ -214,13 +211,13 @@ class Agent:
         with torch.no_grad():
             x_ns = on.features(next_states)
             xs_d = x_s.detach()
-            part2_on, h_on, p_on = on.head().forward(xs_d, x_ns)          # rows [0,B) = s, [B,2B) = s'
+            z_on, h_on, p_on = on.head().forward(xs_d, x_ns)              # rows [0,B) = s, [B,2B) = s'
             if target_noise is None:
                 tg.reset_noise()                                            # agent.py:74
             else:
                 tg.reset_noise(*target_noise)
-            part2_t, _, p_t = tg.head().forward(tg.features(next_states))
-            loss, dz = c51_dueling_loss_grad(p_on, part2_on, p_t, part2_t, actions, returns, nonterminals, weights,
+            z_t, _, _ = tg.head().forward(tg.features(next_states))
+            loss, dz = c51_dueling_loss_grad(z_on, z_t, self.action_space, self.atoms, actions, returns, nonterminals, weights,
                                              self.support, self.Vmin, self.Vmax, self.delta_z, self.discount ** self.n)
             self.optimiser.zero_conv_grad()
             dh = torch.empty((B, 2 * on.hidden_size), dtype=torch.float32, device=self.device)

@@ -63,15 +63,16 @@ __device__ __forceinline__ int col2_of(const HeadDesc& d, int s) { return s == 0
 // ------------------------------------------------------------------------------------------------
 // Forward: C[m][n] (partial over a K slice) = sum_k A[m][k] * W[n][k],  W composed while staging.
 // grid = (n tiles over both streams, k slices, m tiles), block = 128, micro tile (MT/8) x 4.
-// LAYER 1: A = x (two row blocks), N per stream = H, K = K1, out part[ks][m][s*H + n].
-// LAYER 2: A = relu(sum_s' part_in[s'][m][s*H + k] + b1[s][k]), N = Z | A*Z, K = H,
-//          out part[ks][m][col2(s) + n]; the first n tile of each stream also writes h (for backward).
+// LAYER 1: A = x (two row blocks), N per stream = H, K = K1; result h[m][s*H + n] = relu(sum + b1).
+// LAYER 2: A = h, N = Z | A*Z, K = H; result z[m][col2(s) + n] = sum + b2.
+// Split-K: every CTA writes its partial tile part[ks][m][col]; the LAST CTA of an output tile to arrive
+// (atomic ticket, self-resetting) sums the slices in fixed order s = 0..S-1 (deterministic), applies the
+// bias (composed b_mu + b_sigma*eps_out) / ReLU epilogue and writes the final tile.
 // ------------------------------------------------------------------------------------------------
 template <int MT, int LAYER>
 __global__ void __launch_bounds__(HT)
 k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, int m_lo, const float* __restrict__ x_hi,
-          int M, const float* __restrict__ part_in, int s_in, float* __restrict__ part_out, float* __restrict__ h_out,
-          int kslice) {
+          int M, float* __restrict__ part, float* __restrict__ out, int* __restrict__ tickets, int kslice) {
   constexpr int TM = MT / 8;
   constexpr int LDA = MT + 4;
   __shared__ __align__(16) float As[KT][LDA];
@@ -112,20 +113,8 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
         if (LAYER == 1) {
           const float* src = (m < m_lo) ? x_lo + (size_t)m * K : x_hi + (size_t)(m - m_lo) * K;
           v = __ldg(reinterpret_cast<const float4*>(src + k));
-        } else {
-          const int hc = s * d.H + k;
-          for (int sp = 0; sp < s_in; ++sp) {
-            float4 p = __ldg(reinterpret_cast<const float4*>(part_in + ((size_t)sp * M + m) * (2 * d.H) + hc));
-            v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
-          }
-          float4 bm = __ldg(reinterpret_cast<const float4*>(d.b1_mu[s] + k));
-          if (d.eo1[s]) {
-            float4 bs = __ldg(reinterpret_cast<const float4*>(d.b1_sig[s] + k));
-            float4 e = __ldg(reinterpret_cast<const float4*>(d.eo1[s] + k));
-            bm.x = fmaf(bs.x, e.x, bm.x); bm.y = fmaf(bs.y, e.y, bm.y); bm.z = fmaf(bs.z, e.z, bm.z); bm.w = fmaf(bs.w, e.w, bm.w);
-          }
-          v.x = fmaxf(v.x + bm.x, 0.f); v.y = fmaxf(v.y + bm.y, 0.f); v.z = fmaxf(v.z + bm.z, 0.f); v.w = fmaxf(v.w + bm.w, 0.f);
-          if (h_out && n0 == 0) *reinterpret_cast<float4*>(h_out + (size_t)m * (2 * d.H) + hc) = v;
+        } else {  // x_lo = h [M][2H] written by the layer-1 launch
+          v = __ldg(reinterpret_cast<const float4*>(x_lo + (size_t)m * (2 * d.H) + s * d.H + k));
         }
       }
       ra[j] = v;
@@ -191,40 +180,90 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
       __syncthreads();
     }
   }
+  const int S = gridDim.y;
+  if (S > 1) {
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int m = m0 + ty * TM + i;
+      if (m >= M) continue;
+      float* dst = part + ((size_t)blockIdx.y * M + m) * ncols + colbase;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        if (n < Ns) __stcg(dst + n, acc[i][j]);
+      }
+    }
+    // ---- split-K semaphore: the last slice to arrive finishes the tile ----
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      int* t = tickets + blockIdx.z * gridDim.x + blockIdx.x;
+      const int ticket = atomicAdd(t, 1);
+      s_last = (ticket == S - 1);
+      if (s_last) *t = 0;  // leave the counter ready for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int sp = 0; sp < S; ++sp) {
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        const int m = m0 + ty * TM + i;
+        if (m >= M) continue;
+        const float* src = part + ((size_t)sp * M + m) * ncols + colbase;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = n0 + tx * 4 + j;
+          if (n < Ns) acc[i][j] += __ldcg(src + n);
+        }
+      }
+    }
+  }
+  // ---- epilogue: composed bias (+ ReLU for layer 1) ----
+  const float* __restrict__ bmu = (LAYER == 1) ? d.b1_mu[s] : d.b2_mu[s];
+  const float* __restrict__ bsg = (LAYER == 1) ? d.b1_sig[s] : d.b2_sig[s];
+  float bias[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + tx * 4 + j;
+    bias[j] = 0.0f;
+    if (n < Ns) {
+      bias[j] = __ldg(bmu + n);
+      if (eo) bias[j] = fmaf(__ldg(bsg + n), __ldg(eo + n), bias[j]);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + ty * TM + i;
     if (m >= M) continue;
-    float* dst = part_out + ((size_t)blockIdx.y * M + m) * ncols + colbase;
+    float* dst = out + (size_t)m * ncols + colbase;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
-      if (n < Ns) dst[n] = acc[i][j];
+      if (n < Ns) {
+        const float v = acc[i][j] + bias[j];
+        dst[n] = (LAYER == 1) ? fmaxf(v, 0.0f) : v;
+      }
     }
   }
 }
 
-// q[m][a][z] = zv[z] + za[a][z] - mean_a za[.][z]  (model.py:73-75), z = sum of split-K partials + composed bias.
-__device__ __forceinline__ float head_z(const HeadDesc& d, const float* __restrict__ part, int s2, int M, int m, int s,
-                                        int j) {  // j = row within stream s
-  const int ncols = d.Z + d.A * d.Z, col = col2_of(d, s) + j;
-  float v = 0.0f;
-  for (int sp = 0; sp < s2; ++sp) v += __ldg(part + ((size_t)sp * M + m) * ncols + col);
-  float b = __ldg(d.b2_mu[s] + j);
-  if (d.eo2[s]) b = fmaf(__ldg(d.b2_sig[s] + j), __ldg(d.eo2[s] + j), b);
-  return v + b;
-}
-
+// q[m][a][z] = zv[z] + za[a][z] - mean_a za[.][z]  (model.py:73-75) from the head output z[m][Z + A*Z].
 __global__ void __launch_bounds__(128)
-k_head_logits(const __grid_constant__ HeadDesc d, const float* __restrict__ part2, int s2, int M, float* __restrict__ q) {
+k_head_logits(int Z, int A, const float* __restrict__ z, float* __restrict__ q) {
   const int m = blockIdx.x;
-  for (int z = threadIdx.x; z < d.Z; z += blockDim.x) {
-    const float zv = head_z(d, part2, s2, M, m, 0, z);
+  const float* zr = z + (size_t)m * (Z + A * Z);
+  for (int c = threadIdx.x; c < Z; c += blockDim.x) {
     float mean = 0.0f;
-    for (int a = 0; a < d.A; ++a) mean += head_z(d, part2, s2, M, m, 1, a * d.Z + z);
-    mean = mean / (float)d.A;
-    for (int a = 0; a < d.A; ++a)
-      q[((size_t)m * d.A + a) * d.Z + z] = zv + head_z(d, part2, s2, M, m, 1, a * d.Z + z) - mean;
+    for (int a = 0; a < A; ++a) mean += __ldg(zr + Z + a * Z + c);
+    mean = mean / (float)A;
+    const float zv = __ldg(zr + c);
+    for (int a = 0; a < A; ++a) q[((size_t)m * A + a) * Z + c] = zv + __ldg(zr + Z + a * Z + c) - mean;
   }
 }
 
@@ -295,70 +334,78 @@ k_head_wgrad2(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGr
 }
 
 // Layer-2 backward, input gradient with the ReLU mask of layer 1 folded in:
-// dh[m][s*H + k] = (h > 0) * sum_o dz[m][col(o)] * W2_s[o][k].   grid = (H/64, 2), 32 rows per pass.
+// dh[m][s*H + k] = (h > 0) * sum_o dz[m][col(o)] * W2_s[o][k].   grid = (H/32, 2), B <= 32 rows.
+// The CTA's whole [Ns x 32] slab of mu and sigma is fetched with ONE batch of cp.async (all loads in flight
+// at once: a single memory latency instead of one per chunk), dz is staged transposed, W2 is composed
+// on the fly from the raw tiles.
+constexpr int DH_K = 32;
+constexpr int DH_LD = DH_K + 4;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+
 __global__ void __launch_bounds__(HT)
 k_head_dh(const __grid_constant__ HeadDesc d, const float* __restrict__ dz, const float* __restrict__ h, int B,
-          float* __restrict__ dh) {
-  __shared__ __align__(16) float As[32][36];    // dz chunk transposed [o][m]
-  __shared__ __align__(16) float Bs[32][LDB];   // composed W2 chunk [o][k]
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int s = blockIdx.y, k0 = blockIdx.x * NT;
+          float* __restrict__ dh, int ns_pad) {
+  extern __shared__ __align__(16) float smem_dh[];
+  float* Wm = smem_dh;                          // [ns_pad][DH_LD] raw mu
+  float* Wsg = Wm + (size_t)ns_pad * DH_LD;     // [ns_pad][DH_LD] raw sigma
+  float* Dt = Wsg + (size_t)ns_pad * DH_LD;     // [ns_pad][36]    dz transposed [o][m]
+  const int tid = threadIdx.x, tk = tid & 7, tm = tid >> 3;  // micro tile: 2 rows (m) x 4 k
+  const int s = blockIdx.y, k0 = blockIdx.x * DH_K;
   const int Ns = n2_of(d, s), colbase = col2_of(d, s), ncols = d.Z + d.A * d.Z;
   const float* ei = d.ei2[s];
   const float* eo = d.eo2[s];
-  for (int mb = 0; mb < B; mb += 32) {
-    float acc[4][4];
+  float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ei) e4 = __ldg(reinterpret_cast<const float4*>(ei + k0 + tk * 4));
+  float acc[2][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-    for (int ob = 0; ob < Ns; ob += 32) {
-      for (int idx = tid; idx < 32 * 32; idx += HT) {
-        const int mm = idx >> 5, oo = idx & 31, m = mb + mm, o = ob + oo;
-        As[oo][mm] = (m < B && o < Ns) ? __ldg(dz + (size_t)m * ncols + colbase + o) : 0.0f;
-      }
-      for (int idx = tid; idx < 32 * (NT / 4); idx += HT) {
-        const int oo = idx >> 4, k = k0 + (idx & 15) * 4, o = ob + oo;
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (o < Ns && k < d.H) {
-          w = __ldg(reinterpret_cast<const float4*>(d.w2_mu[s] + (size_t)o * d.H + k));
-          if (ei) {
-            const float4 sg = __ldg(reinterpret_cast<const float4*>(d.w2_sig[s] + (size_t)o * d.H + k));
-            const float4 e4 = __ldg(reinterpret_cast<const float4*>(ei + k));
-            const float e = __ldg(eo + o);
-            w.x = fmaf(sg.x, e * e4.x, w.x); w.y = fmaf(sg.y, e * e4.y, w.y);
-            w.z = fmaf(sg.z, e * e4.z, w.z); w.w = fmaf(sg.w, e * e4.w, w.w);
-          }
-        }
-        *reinterpret_cast<float4*>(&Bs[oo][(idx & 15) * 4]) = w;
-      }
-      __syncthreads();
-#pragma unroll 8
-      for (int oo = 0; oo < 32; ++oo) {
-        const float4 a = *reinterpret_cast<const float4*>(&As[oo][ty * 4]);
-        const float4 b = *reinterpret_cast<const float4*>(&Bs[oo][tx * 4]);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          acc[i][0] = fmaf(av[i], b.x, acc[i][0]); acc[i][1] = fmaf(av[i], b.y, acc[i][1]);
-          acc[i][2] = fmaf(av[i], b.z, acc[i][2]); acc[i][3] = fmaf(av[i], b.w, acc[i][3]);
-        }
-      }
-      __syncthreads();
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  for (int ob = 0; ob < Ns; ob += ns_pad) {  // one pass unless actions*atoms exceeds the slab (ns_pad rows)
+  const int nb = min(ns_pad, Ns - ob);
+  if (ob) __syncthreads();
+  for (int idx = tid; idx < nb * (DH_K / 4); idx += HT) {
+    const int o = idx >> 3, k4 = (idx & 7) * 4;
+    cp_async16(Wm + (size_t)o * DH_LD + k4, d.w2_mu[s] + (size_t)(ob + o) * d.H + k0 + k4);
+    if (ei) cp_async16(Wsg + (size_t)o * DH_LD + k4, d.w2_sig[s] + (size_t)(ob + o) * d.H + k0 + k4);
+  }
+  for (int idx = tid; idx < 32 * nb; idx += HT) {
+    const int m = idx / nb, o = idx - m * nb;
+    Dt[(size_t)o * 36 + m] = (m < B) ? __ldg(dz + (size_t)m * ncols + colbase + ob + o) : 0.0f;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+#pragma unroll 4
+  for (int o = 0; o < nb; ++o) {
+    float4 w = *reinterpret_cast<const float4*>(Wm + (size_t)o * DH_LD + tk * 4);
+    if (ei) {
+      const float4 sg = *reinterpret_cast<const float4*>(Wsg + (size_t)o * DH_LD + tk * 4);
+      const float e = __ldg(eo + ob + o);
+      w.x = fmaf(sg.x, e * e4.x, w.x); w.y = fmaf(sg.y, e * e4.y, w.y);
+      w.z = fmaf(sg.z, e * e4.z, w.z); w.w = fmaf(sg.w, e * e4.w, w.w);
     }
+    const float2 a = *reinterpret_cast<const float2*>(Dt + (size_t)o * 36 + tm * 2);
+    acc[0][0] = fmaf(a.x, w.x, acc[0][0]); acc[0][1] = fmaf(a.x, w.y, acc[0][1]);
+    acc[0][2] = fmaf(a.x, w.z, acc[0][2]); acc[0][3] = fmaf(a.x, w.w, acc[0][3]);
+    acc[1][0] = fmaf(a.y, w.x, acc[1][0]); acc[1][1] = fmaf(a.y, w.y, acc[1][1]);
+    acc[1][2] = fmaf(a.y, w.z, acc[1][2]); acc[1][3] = fmaf(a.y, w.w, acc[1][3]);
+  }
+  }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int m = mb + ty * 4 + i;
-      if (m >= B) continue;
-      const int k = k0 + tx * 4;
-      if (k >= d.H) continue;
-      const size_t off = (size_t)m * (2 * d.H) + s * d.H + k;
-      const float4 hv = __ldg(reinterpret_cast<const float4*>(h + off));
-      float4 o4;
-      o4.x = hv.x > 0.f ? acc[i][0] : 0.f; o4.y = hv.y > 0.f ? acc[i][1] : 0.f;
-      o4.z = hv.z > 0.f ? acc[i][2] : 0.f; o4.w = hv.w > 0.f ? acc[i][3] : 0.f;
-      *reinterpret_cast<float4*>(dh + off) = o4;
-    }
+  for (int i = 0; i < 2; ++i) {
+    const int m = tm * 2 + i;
+    if (m >= B) continue;
+    const size_t off = (size_t)m * (2 * d.H) + s * d.H + k0 + tk * 4;
+    const float4 hv = __ldg(reinterpret_cast<const float4*>(h + off));
+    float4 o4;
+    o4.x = hv.x > 0.f ? acc[i][0] : 0.f; o4.y = hv.y > 0.f ? acc[i][1] : 0.f;
+    o4.z = hv.z > 0.f ? acc[i][2] : 0.f; o4.w = hv.w > 0.f ? acc[i][3] : 0.f;
+    *reinterpret_cast<float4*>(dh + off) = o4;
   }
 }
 
@@ -368,11 +415,14 @@ k_head_dh(const __grid_constant__ HeadDesc d, const float* __restrict__ dz, cons
 // and the input gradient  dx[m][k] = sum_s sum_o dh[m][s*H+o] * W1_s[o][k].
 // grid = (K1/32, 2 streams) launched as clusters of 2 CTAs along y: the advantage-stream CTA hands its
 // dx partial to the value-stream CTA through distributed shared memory (fixed order -> deterministic).
+// 256 threads: warps 0-3 compute the weight-gradient tile of the current 32-row chunk of W1 while warps
+// 4-7 accumulate the input gradient from the same staged tiles; all 8 warps prefetch the next chunk.
 // ------------------------------------------------------------------------------------------------
-constexpr int B1_K = 32;  // k columns per CTA
-constexpr int B1_O = 32;  // rows of W1 per chunk
+constexpr int B1_K = 32;   // k columns per CTA
+constexpr int B1_O = 32;   // rows of W1 per chunk
+constexpr int B1_T = 256;  // threads
 
-__global__ void __cluster_dims__(1, 2, 1) __launch_bounds__(HT)
+__global__ void __cluster_dims__(1, 2, 1) __launch_bounds__(B1_T)
 k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrads g, const float* __restrict__ x,
             const float* __restrict__ dh, int B, float* __restrict__ dx) {
   __shared__ __align__(16) float Xs[32][B1_K + 4];    // x slice [m][k]
@@ -380,120 +430,119 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
   __shared__ __align__(16) float DsT[B1_O][32 + 4];   // dh chunk [o][m]
   __shared__ __align__(16) float Ws[B1_O][B1_K + 4];  // composed W1 chunk [o][k]
   __shared__ __align__(16) float Red[32][B1_K + 4];   // dx partial handed over the cluster
+  __shared__ float Eo[B1_O];                          // eps_out of the chunk's rows
   cg::cluster_group cluster = cg::this_cluster();
-  const int tid = threadIdx.x, tk = tid & 15, to = tid >> 4;  // micro tile: 4 rows (o or m) x 2 k
+  const int tid = threadIdx.x;
+  const int role = tid >> 7, rt = tid & 127, tk = rt & 15, to = rt >> 4;  // micro tile: 4 rows (o or m) x 2 k
   const int s = blockIdx.y, k0 = blockIdx.x * B1_K, K = d.K1, H = d.H;
   const float* __restrict__ mu = d.w1_mu[s];
   const float* __restrict__ sg = d.w1_sig[s];
   const float* ei = d.ei1[s];
   const float* eo = d.eo1[s];
 
-  for (int idx = tid; idx < 32 * (B1_K / 4); idx += HT) {
-    const int m = idx >> 3, kk = (idx & 7) * 4;
+  {  // x slice: 32 rows x 8 float4 = 256 float4, one per thread
+    const int m = tid >> 3, kk = (tid & 7) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (m < B) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)m * K + k0 + kk));
     *reinterpret_cast<float4*>(&Xs[m][kk]) = v;
   }
   const float ei0 = ei ? __ldg(ei + k0 + tk * 2) : 0.0f, ei1v = ei ? __ldg(ei + k0 + tk * 2 + 1) : 0.0f;
+  // staging coordinates of this thread (one float4 of mu, sigma, dh per chunk)
+  const int st_r = tid >> 3, st_c = (tid & 7) * 4;
+  float4 e4s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ei) e4s = __ldg(reinterpret_cast<const float4*>(ei + k0 + st_c));
 
-  float dxa[4][2];
+  float acc[4][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) dxa[i][0] = dxa[i][1] = 0.0f;
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0f;
 
-  // register prefetch of the next chunk: 32x32 mu, sigma (2 float4 each per thread) and 32x32 dh (2 float4)
-  float4 pmu[2], psg[2], pdh[2];
+  float4 pmu, psg, pdh;
+  float peo = 0.0f;
   auto prefetch = [&](int ob) {
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int idx = tid + j * HT, oo = idx >> 3, kk = (idx & 7) * 4, o = ob + oo;
-      pmu[j] = __ldg(reinterpret_cast<const float4*>(mu + (size_t)o * K + k0 + kk));
-      psg[j] = ei ? __ldg(reinterpret_cast<const float4*>(sg + (size_t)o * K + k0 + kk)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const int m = idx >> 3, o4 = (idx & 7) * 4;
-      pdh[j] = (m < B) ? __ldg(reinterpret_cast<const float4*>(dh + (size_t)m * (2 * H) + s * H + ob + o4))
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    pmu = __ldg(reinterpret_cast<const float4*>(mu + (size_t)(ob + st_r) * K + k0 + st_c));
+    psg = ei ? __ldg(reinterpret_cast<const float4*>(sg + (size_t)(ob + st_r) * K + k0 + st_c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    pdh = (st_r < B) ? __ldg(reinterpret_cast<const float4*>(dh + (size_t)st_r * (2 * H) + s * H + ob + st_c))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    peo = eo ? __ldg(eo + ob + st_r) : 0.0f;
   };
-  auto commit = [&](int ob) {
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int idx = tid + j * HT, oo = idx >> 3, kk = (idx & 7) * 4, o = ob + oo;
-      float4 w = pmu[j];
-      if (ei) {
-        const float e = __ldg(eo + o);
-        const float4 e4 = __ldg(reinterpret_cast<const float4*>(ei + k0 + kk));
-        w.x = fmaf(psg[j].x, e * e4.x, w.x); w.y = fmaf(psg[j].y, e * e4.y, w.y);
-        w.z = fmaf(psg[j].z, e * e4.z, w.z); w.w = fmaf(psg[j].w, e * e4.w, w.w);
-      }
-      *reinterpret_cast<float4*>(&Ws[oo][kk]) = w;
-      const int m = idx >> 3, o4 = (idx & 7) * 4;
-      *reinterpret_cast<float4*>(&Ds[m][o4]) = pdh[j];
-      DsT[o4 + 0][m] = pdh[j].x; DsT[o4 + 1][m] = pdh[j].y; DsT[o4 + 2][m] = pdh[j].z; DsT[o4 + 3][m] = pdh[j].w;
+  auto commit = [&]() {
+    float4 w = pmu;
+    if (ei) {
+      w.x = fmaf(psg.x, peo * e4s.x, w.x); w.y = fmaf(psg.y, peo * e4s.y, w.y);
+      w.z = fmaf(psg.z, peo * e4s.z, w.z); w.w = fmaf(psg.w, peo * e4s.w, w.w);
     }
+    *reinterpret_cast<float4*>(&Ws[st_r][st_c]) = w;
+    *reinterpret_cast<float4*>(&Ds[st_r][st_c]) = pdh;
+    DsT[st_c + 0][st_r] = pdh.x; DsT[st_c + 1][st_r] = pdh.y; DsT[st_c + 2][st_r] = pdh.z; DsT[st_c + 3][st_r] = pdh.w;
+    if (st_c == 0) Eo[st_r] = peo;
   };
 
   prefetch(0);
-  commit(0);
+  commit();
   __syncthreads();
   for (int ob = 0; ob < H; ob += B1_O) {
     const bool more = ob + B1_O < H;
     if (more) prefetch(ob + B1_O);
-    // ---- weight gradient tile [32 o][32 k]: reduction over the batch rows ----
-    float ga[4][2];
+    if (role == 0) {
+      // ---- weight gradient tile [32 o][32 k]: reduction over the batch rows ----
+      float ga[4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ga[i][0] = ga[i][1] = 0.0f;
+      for (int i = 0; i < 4; ++i) ga[i][0] = ga[i][1] = 0.0f;
 #pragma unroll 8
-    for (int m = 0; m < 32; ++m) {
-      const float4 a = *reinterpret_cast<const float4*>(&Ds[m][to * 4]);
-      const float2 b = *reinterpret_cast<const float2*>(&Xs[m][tk * 2]);
-      ga[0][0] = fmaf(a.x, b.x, ga[0][0]); ga[0][1] = fmaf(a.x, b.y, ga[0][1]);
-      ga[1][0] = fmaf(a.y, b.x, ga[1][0]); ga[1][1] = fmaf(a.y, b.y, ga[1][1]);
-      ga[2][0] = fmaf(a.z, b.x, ga[2][0]); ga[2][1] = fmaf(a.z, b.y, ga[2][1]);
-      ga[3][0] = fmaf(a.w, b.x, ga[3][0]); ga[3][1] = fmaf(a.w, b.y, ga[3][1]);
-    }
+      for (int m = 0; m < 32; ++m) {
+        const float4 a = *reinterpret_cast<const float4*>(&Ds[m][to * 4]);
+        const float2 b = *reinterpret_cast<const float2*>(&Xs[m][tk * 2]);
+        ga[0][0] = fmaf(a.x, b.x, ga[0][0]); ga[0][1] = fmaf(a.x, b.y, ga[0][1]);
+        ga[1][0] = fmaf(a.y, b.x, ga[1][0]); ga[1][1] = fmaf(a.y, b.y, ga[1][1]);
+        ga[2][0] = fmaf(a.z, b.x, ga[2][0]); ga[2][1] = fmaf(a.z, b.y, ga[2][1]);
+        ga[3][0] = fmaf(a.w, b.x, ga[3][0]); ga[3][1] = fmaf(a.w, b.y, ga[3][1]);
+      }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int o = ob + to * 4 + i;
-      const size_t off = (size_t)o * K + k0 + tk * 2;
-      *reinterpret_cast<float2*>(g.w1_mu[s] + off) = make_float2(ga[i][0], ga[i][1]);
-      const float e = ei ? __ldg(eo + o) : 0.0f;
-      *reinterpret_cast<float2*>(g.w1_sig[s] + off) = make_float2(ga[i][0] * (e * ei0), ga[i][1] * (e * ei1v));
-    }
-    if (blockIdx.x == 0 && tid < B1_O) {  // bias gradients of this chunk's rows
-      float bs = 0.0f;
-      for (int m = 0; m < 32; ++m) bs += Ds[m][tid];
-      g.b1_mu[s][ob + tid] = bs;
-      g.b1_sig[s][ob + tid] = eo ? bs * __ldg(eo + ob + tid) : 0.0f;
-    }
-    // ---- input gradient [32 m][32 k]: reduction over this chunk's rows of W1 ----
+      for (int i = 0; i < 4; ++i) {
+        const int o = ob + to * 4 + i;
+        const size_t off = (size_t)o * K + k0 + tk * 2;
+        __stcs(reinterpret_cast<float2*>(g.w1_mu[s] + off), make_float2(ga[i][0], ga[i][1]));
+        const float e = Eo[to * 4 + i];
+        __stcs(reinterpret_cast<float2*>(g.w1_sig[s] + off), make_float2(ga[i][0] * (e * ei0), ga[i][1] * (e * ei1v)));
+      }
+      if (blockIdx.x == 0 && rt < B1_O) {  // bias gradients of this chunk's rows
+        float bs = 0.0f;
+        for (int m = 0; m < 32; ++m) bs += Ds[m][rt];
+        g.b1_mu[s][ob + rt] = bs;
+        g.b1_sig[s][ob + rt] = bs * Eo[rt];
+      }
+    } else {
+      // ---- input gradient [32 m][32 k]: reduction over this chunk's rows of W1 ----
 #pragma unroll 8
-    for (int oo = 0; oo < B1_O; ++oo) {
-      const float4 a = *reinterpret_cast<const float4*>(&DsT[oo][to * 4]);
-      const float2 b = *reinterpret_cast<const float2*>(&Ws[oo][tk * 2]);
-      dxa[0][0] = fmaf(a.x, b.x, dxa[0][0]); dxa[0][1] = fmaf(a.x, b.y, dxa[0][1]);
-      dxa[1][0] = fmaf(a.y, b.x, dxa[1][0]); dxa[1][1] = fmaf(a.y, b.y, dxa[1][1]);
-      dxa[2][0] = fmaf(a.z, b.x, dxa[2][0]); dxa[2][1] = fmaf(a.z, b.y, dxa[2][1]);
-      dxa[3][0] = fmaf(a.w, b.x, dxa[3][0]); dxa[3][1] = fmaf(a.w, b.y, dxa[3][1]);
+      for (int oo = 0; oo < B1_O; ++oo) {
+        const float4 a = *reinterpret_cast<const float4*>(&DsT[oo][to * 4]);
+        const float2 b = *reinterpret_cast<const float2*>(&Ws[oo][tk * 2]);
+        acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+        acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+        acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]);
+        acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]);
+      }
     }
     __syncthreads();
     if (more) {
-      commit(ob + B1_O);
+      commit();
       __syncthreads();
     }
   }
   // ---- dx = value-stream partial + advantage-stream partial, over distributed shared memory ----
-  if (s == 1) {
+  if (s == 1 && role == 1) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) *reinterpret_cast<float2*>(&Red[to * 4 + i][tk * 2]) = make_float2(dxa[i][0], dxa[i][1]);
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<float2*>(&Red[to * 4 + i][tk * 2]) = make_float2(acc[i][0], acc[i][1]);
   }
   cluster.sync();
-  if (s == 0) {
+  if (s == 0 && role == 1) {
     const float* remote = cluster.map_shared_rank(&Red[0][0], 1);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int m = to * 4 + i;
       if (m < B) {
         const float2 r = *reinterpret_cast<const float2*>(remote + m * (B1_K + 4) + tk * 2);
-        *reinterpret_cast<float2*>(dx + (size_t)m * K + k0 + tk * 2) = make_float2(dxa[i][0] + r.x, dxa[i][1] + r.y);
+        *reinterpret_cast<float2*>(dx + (size_t)m * K + k0 + tk * 2) = make_float2(acc[i][0] + r.x, acc[i][1] + r.y);
       }
     }
   }
@@ -579,47 +628,45 @@ int rb_head_splits(int conv_features, int hidden, int* s1, int* s2) {
   return RB_OK;
 }
 
-int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const float* x_hi, int m_hi, float* part1, float* h,
-                    float* part2, rb_stream_t stream) {
+int rb_head_ticket_count(void) { return 4096; }
+
+int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const float* x_hi, int m_hi, float* part1, float* part2,
+                    int32_t* tickets, float* h, float* z, rb_stream_t stream) {
   int rc = head_check(p, "rb_head_forward: null pointer or bad size");
   if (rc != RB_OK) return rc;
   const int M = m_lo + m_hi;
-  if (!x_lo || m_lo <= 0 || m_hi < 0 || (m_hi > 0 && !x_hi) || !part1 || !part2) return rbi::fail(RB_ERR_INVAL, "rb_head_forward: bad argument");
-  if (M > 65535) return rbi::fail(RB_ERR_RANGE, "rb_head_forward: too many rows");
+  if (!x_lo || m_lo <= 0 || m_hi < 0 || (m_hi > 0 && !x_hi) || !part1 || !part2 || !tickets || !h || !z)
+    return rbi::fail(RB_ERR_INVAL, "rb_head_forward: bad argument");
   const HeadDesc d = to_desc(p);
   int s1, s2, ks1, ks2;
   head_splits(d.K1, d.H, &s1, &s2, &ks1, &ks2);
   cudaStream_t st = (cudaStream_t)stream;
   const int MT = (M > 32) ? 64 : 32;
   const int mt = (M + MT - 1) / MT;
+  const int tiles1 = 2 * d.H / NT, tiles2 = (d.Z + NT - 1) / NT + (d.A * d.Z + NT - 1) / NT;
+  if (mt > 65535 || mt * tiles1 > 2048 || mt * tiles2 > 2048) return rbi::fail(RB_ERR_RANGE, "rb_head_forward: too many rows");
   {
-    dim3 grid(2 * d.H / NT, s1, mt);
+    dim3 grid(tiles1, s1, mt);
     rbi::ProfScope prof_(RB_K_HEAD_FC1, st);
-    if (MT == 64) k_head_fc<64, 1><<<grid, HT, 0, st>>>(d, x_lo, m_lo, x_hi, M, nullptr, 0, part1, nullptr, ks1);
-    else k_head_fc<32, 1><<<grid, HT, 0, st>>>(d, x_lo, m_lo, x_hi, M, nullptr, 0, part1, nullptr, ks1);
+    if (MT == 64) k_head_fc<64, 1><<<grid, HT, 0, st>>>(d, x_lo, m_lo, x_hi, M, part1, h, tickets, ks1);
+    else k_head_fc<32, 1><<<grid, HT, 0, st>>>(d, x_lo, m_lo, x_hi, M, part1, h, tickets, ks1);
   }
   rc = rbi::check_launch("rb_head_forward(fc1)");
   if (rc != RB_OK) return rc;
   {
-    const int tiles = (d.Z + NT - 1) / NT + (d.A * d.Z + NT - 1) / NT;
-    dim3 grid(tiles, s2, mt);
+    dim3 grid(tiles2, s2, mt);
     rbi::ProfScope prof_(RB_K_HEAD_FC2, st);
-    if (MT == 64) k_head_fc<64, 2><<<grid, HT, 0, st>>>(d, nullptr, 0, nullptr, M, part1, s1, part2, h, ks2);
-    else k_head_fc<32, 2><<<grid, HT, 0, st>>>(d, nullptr, 0, nullptr, M, part1, s1, part2, h, ks2);
+    if (MT == 64) k_head_fc<64, 2><<<grid, HT, 0, st>>>(d, h, M, nullptr, M, part2, z, tickets + 2048, ks2);
+    else k_head_fc<32, 2><<<grid, HT, 0, st>>>(d, h, M, nullptr, M, part2, z, tickets + 2048, ks2);
   }
   return rbi::check_launch("rb_head_forward(fc2)");
 }
 
-int rb_head_logits(const rb_head_params* p, const float* part2, int M, float* q, rb_stream_t stream) {
-  int rc = head_check(p, "rb_head_logits: null pointer or bad size");
-  if (rc != RB_OK) return rc;
-  if (!part2 || !q || M <= 0) return rbi::fail(RB_ERR_INVAL, "rb_head_logits: bad argument");
-  const HeadDesc d = to_desc(p);
-  int s1, s2, ks1, ks2;
-  head_splits(d.K1, d.H, &s1, &s2, &ks1, &ks2);
+int rb_head_logits(const float* z, int M, int actions, int atoms, float* q, rb_stream_t stream) {
+  if (!z || !q || M <= 0 || actions <= 0 || atoms <= 0) return rbi::fail(RB_ERR_INVAL, "rb_head_logits: bad argument");
   {
     rbi::ProfScope prof_(RB_K_HEAD_LOGITS, (cudaStream_t)stream);
-    k_head_logits<<<M, 128, 0, (cudaStream_t)stream>>>(d, part2, s2, M, q);
+    k_head_logits<<<M, 128, 0, (cudaStream_t)stream>>>(atoms, actions, z, q);
   }
   return rbi::check_launch("rb_head_logits");
 }
@@ -649,16 +696,24 @@ int rb_head_backward(const rb_head_params* p, const rb_head_grads* gr, const flo
   rc = rbi::check_launch("rb_head_backward(wgrad2)");
   if (rc != RB_OK) return rc;
   {
-    dim3 grid(d.H / NT, 2);
+    const int ns_max = d.A * d.Z > d.Z ? d.A * d.Z : d.Z;
+    int ns_pad = (ns_max + 3) & ~3;
+    if (ns_pad > 384) ns_pad = 384;
+    const size_t smem = (size_t)ns_pad * (2 * DH_LD + 36) * sizeof(float);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(k_head_dh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return rbi::fail(RB_ERR_CUDA, cudaGetErrorString(e));
+    }
+    dim3 grid(d.H / DH_K, 2);
     rbi::ProfScope prof_(RB_K_HEAD_DH, st);
-    k_head_dh<<<grid, HT, 0, st>>>(d, dz, h, B, dh_scratch);
+    k_head_dh<<<grid, HT, smem, st>>>(d, dz, h, B, dh_scratch, ns_pad);
   }
   rc = rbi::check_launch("rb_head_backward(dh)");
   if (rc != RB_OK) return rc;
   {
     dim3 grid(d.K1 / B1_K, 2);
     rbi::ProfScope prof_(RB_K_HEAD_BWD1, st);
-    k_head_bwd1<<<grid, HT, 0, st>>>(d, g, x, dh_scratch, B, dx);
+    k_head_bwd1<<<grid, B1_T, 0, st>>>(d, g, x, dh_scratch, B, dx);
   }
   return rbi::check_launch("rb_head_backward(bwd1)");
 }

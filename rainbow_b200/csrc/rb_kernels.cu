@@ -663,71 +663,72 @@ k_c51(const float* __restrict__ q_on_s, const float* __restrict__ q_on_ns, const
   }
 }
 
-// Dueling entry point: logits are rebuilt per sample from the fused head's split-K partial outputs
-// (z = sum of partials + composed bias; q[a][z] = zv[z] + za[a][z] - mean_a za[.][z], model.py:73-75) in
-// warp-private shared memory, and the gradient is returned w.r.t. the head outputs:
-// dzv[z] = g[z],  dza[a][z] = g[z] * ([a == act] - 1/A).
-struct DuelSide {  // one network's head output
-  const float* part2;    // [s2][rows][Z + A*Z]
-  const float* b2_mu[2];
-  const float* b2_sig[2];
-  const float* eo2[2];   // null in eval mode
-  int s2, rows;
-};
-
-__device__ __forceinline__ float duel_z(const DuelSide& d, int Z, int A, int row, int s, int j) {
-  const int ncols = Z + A * Z, col = (s == 0 ? 0 : Z) + j;
-  float v = 0.0f;
-  for (int sp = 0; sp < d.s2; ++sp) v += __ldg(d.part2 + ((size_t)sp * d.rows + row) * ncols + col);
-  float b = __ldg(d.b2_mu[s] + j);
-  if (d.eo2[s]) b = fmaf(__ldg(d.b2_sig[s] + j), __ldg(d.eo2[s] + j), b);
-  return v + b;
-}
-
-// fills q[a][z] for a in [0,A) (or only row `only_a` into q[0][z] when only_a >= 0)
-__device__ __forceinline__ void duel_rows(const DuelSide& d, int Z, int A, int row, int lane, float* q, int only_a) {
-  for (int z = lane; z < Z; z += 32) {
-    const float zv = duel_z(d, Z, A, row, 0, z);
-    float mean = 0.0f;
-    for (int a = 0; a < A; ++a) mean += duel_z(d, Z, A, row, 1, a * Z + z);
-    mean = mean / (float)A;
-    if (only_a >= 0) {
-      q[z] = zv + duel_z(d, Z, A, row, 1, only_a * Z + z) - mean;
-    } else {
-      for (int a = 0; a < A; ++a) q[(size_t)a * Z + z] = zv + duel_z(d, Z, A, row, 1, a * Z + z) - mean;
-    }
-  }
-}
-
+// Dueling entry point: fed by the fused heads' outputs z = (z_value | z_advantage) [rows][Z + A*Z]
+// (online net: 2B rows, s then s'; target net: B rows).  The CTA stages the z rows of its four samples in
+// shared memory with coalesced loads, each warp assembles its logit rows
+// q[a][z] = zv[z] + za[a][z] - mean_a za[.][z] (model.py:73-75) there, and the gradient is returned w.r.t.
+// the head outputs:  dzv[z] = g[z],  dza[a][z] = g[z] * ([a == act] - 1/A).
 __global__ void __launch_bounds__(C51_WARPS * 32)
-k_c51_dueling(const __grid_constant__ DuelSide on, const __grid_constant__ DuelSide tg, const int64_t* __restrict__ actions,
+k_c51_dueling(const float* __restrict__ z_on, const float* __restrict__ z_tg, const int64_t* __restrict__ actions,
               const float* __restrict__ returns, const float* __restrict__ nonterminals, const float* __restrict__ weights,
               const float* __restrict__ support, float vmin, float vmax, float delta_z, float gamma_n, int B, int A, int Z,
               float* __restrict__ loss, float* __restrict__ dz, float* __restrict__ m_out, int64_t* __restrict__ astar_out) {
-  extern __shared__ __align__(16) float s_dyn[];  // per warp: q_on_ns [A*Z], q_tg [A*Z], q_on_s_act [Z]
+  extern __shared__ __align__(16) float s_dyn[];
   __shared__ C51Scratch s_sc[C51_WARPS];
+  const int N2 = Z + A * Z;
+  // layout: zs[C51_WARPS][3][N2] (online s, online s', target s'), then per warp q rows [2*A*Z + Z]
+  float* zs = s_dyn;
+  float* qs = s_dyn + (size_t)C51_WARPS * 3 * N2;
+  const int i0 = blockIdx.x * C51_WARPS;
+  for (int idx = threadIdx.x; idx < C51_WARPS * 3 * N2; idx += blockDim.x) {
+    const int w = idx / (3 * N2), rem = idx - w * 3 * N2, t = rem / N2, c = rem - t * N2, i = i0 + w;
+    float v = 0.0f;
+    if (i < B) v = (t == 0) ? __ldg(z_on + (size_t)i * N2 + c) : (t == 1) ? __ldg(z_on + (size_t)(B + i) * N2 + c) : __ldg(z_tg + (size_t)i * N2 + c);
+    zs[idx] = v;
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * C51_WARPS + warp;
+  const int i = i0 + warp;
   if (i >= B) return;
-  float* q_ns = s_dyn + (size_t)warp * (2 * A * Z + Z);
+  const float* zw = zs + (size_t)warp * 3 * N2;
+  float* q_ns = qs + (size_t)warp * (2 * A * Z + Z);
   float* q_t = q_ns + A * Z;
   float* q_s = q_t + A * Z;
   const int act = (int)actions[i];
-  duel_rows(on, Z, A, B + i, lane, q_ns, -1);  // online(s'): rows B..2B-1 of the batched online pass
-  duel_rows(tg, Z, A, i, lane, q_t, -1);       // target(s')
-  duel_rows(on, Z, A, i, lane, q_s, act);      // online(s), taken action only
+  const float inv_a = 1.0f / (float)A;
+  for (int c = lane; c < Z; c += 32) {
+    {  // online(s): the taken action only
+      const float* r = zw;
+      float mean = 0.0f;
+      for (int a = 0; a < A; ++a) mean += r[Z + a * Z + c];
+      q_s[c] = r[c] + r[Z + act * Z + c] - mean / (float)A;
+    }
+    {  // online(s')
+      const float* r = zw + N2;
+      float mean = 0.0f;
+      for (int a = 0; a < A; ++a) mean += r[Z + a * Z + c];
+      mean = mean / (float)A;
+      for (int a = 0; a < A; ++a) q_ns[a * Z + c] = r[c] + r[Z + a * Z + c] - mean;
+    }
+    {  // target(s')
+      const float* r = zw + 2 * N2;
+      float mean = 0.0f;
+      for (int a = 0; a < A; ++a) mean += r[Z + a * Z + c];
+      mean = mean / (float)A;
+      for (int a = 0; a < A; ++a) q_t[a * Z + c] = r[c] + r[Z + a * Z + c] - mean;
+    }
+  }
   __syncwarp();
   float g[C51_R];
   c51_core(s_sc[warp], lane, i, B, A, Z, q_ns, q_t, q_s, __ldg(returns + i), __ldg(nonterminals + i), __ldg(weights + i),
            support, vmin, vmax, delta_z, gamma_n, loss, m_out, astar_out, g);
-  float* dzi = dz + (size_t)i * (Z + A * Z);
-  const float inv_a = 1.0f / (float)A;
+  float* dzi = dz + (size_t)i * N2;
 #pragma unroll
   for (int r = 0; r < C51_R; ++r) {
-    const int z = lane + 32 * r;
-    if (z < Z) {
-      dzi[z] = g[r];
-      for (int a = 0; a < A; ++a) dzi[Z + a * Z + z] = g[r] * ((a == act ? 1.0f : 0.0f) - inv_a);
+    const int c = lane + 32 * r;
+    if (c < Z) {
+      dzi[c] = g[r];
+      for (int a = 0; a < A; ++a) dzi[Z + a * Z + c] = g[r] * ((a == act ? 1.0f : 0.0f) - inv_a);
     }
   }
 }
@@ -1143,41 +1144,26 @@ int rb_noisy_outer(float* const* weight_eps, float* const* bias_eps, const int* 
   return noisy_launch(weight_eps, bias_eps, in_features, out_features, n_layers, f_in, f_out, 0, nullptr, 1, stream);
 }
 
-int rb_c51_dueling_loss_grad(const rb_head_params* online, const float* part2_online, const rb_head_params* target,
-                             const float* part2_target, const int64_t* actions, const float* returns,
-                             const float* nonterminals, const float* weights, const float* support, float vmin, float vmax,
-                             float delta_z, float gamma_n, int B, float* loss, float* dz, float* m_out, int64_t* astar_out,
-                             rb_stream_t stream) {
-  if (!online || !target || !part2_online || !part2_target || !actions || !returns || !nonterminals || !weights || !support ||
-      !loss || !dz)
+int rb_c51_dueling_loss_grad(const float* z_online, const float* z_target, int actions_n, int atoms, const int64_t* actions,
+                             const float* returns, const float* nonterminals, const float* weights, const float* support,
+                             float vmin, float vmax, float delta_z, float gamma_n, int B, float* loss, float* dz, float* m_out,
+                             int64_t* astar_out, rb_stream_t stream) {
+  if (!z_online || !z_target || !actions || !returns || !nonterminals || !weights || !support || !loss || !dz)
     return fail(RB_ERR_INVAL, "rb_c51_dueling_loss_grad: null pointer");
-  const int Z = online->atoms, A = online->actions;
-  if (B <= 0 || A <= 0 || Z <= 1 || target->atoms != Z || target->actions != A || target->hidden != online->hidden ||
-      target->conv_features != online->conv_features)
-    return fail(RB_ERR_INVAL, "rb_c51_dueling_loss_grad: inconsistent sizes");
-  if (Z > RB_MAX_ATOMS) return fail(RB_ERR_RANGE, "rb_c51_dueling_loss_grad: Z exceeds RB_MAX_ATOMS");
-  int s1 = 0, s2 = 0;
-  int rc = rb_head_splits(online->conv_features, online->hidden, &s1, &s2);
-  if (rc != RB_OK) return rc;
-  DuelSide on, tg;
-  for (int s = 0; s < 2; ++s) {
-    on.b2_mu[s] = online->b2_mu[s]; on.b2_sig[s] = online->b2_sigma[s]; on.eo2[s] = online->eps_out2[s];
-    tg.b2_mu[s] = target->b2_mu[s]; tg.b2_sig[s] = target->b2_sigma[s]; tg.eo2[s] = target->eps_out2[s];
-    if (!on.b2_mu[s] || !on.b2_sig[s] || !tg.b2_mu[s] || !tg.b2_sig[s]) return fail(RB_ERR_INVAL, "rb_c51_dueling_loss_grad: null bias pointer");
-  }
-  on.part2 = part2_online; on.s2 = s2; on.rows = 2 * B;
-  tg.part2 = part2_target; tg.s2 = s2; tg.rows = B;
-  const size_t smem = (size_t)C51_WARPS * (2 * A * Z + Z) * sizeof(float);
-  if (smem > 160 * 1024) return fail(RB_ERR_RANGE, "rb_c51_dueling_loss_grad: actions * atoms too large");
+  const int Z = atoms, A = actions_n;
+  if (B <= 0 || A <= 0 || Z <= 1) return fail(RB_ERR_INVAL, "rb_c51_dueling_loss_grad: B, actions > 0 and atoms > 1 are required");
+  if (Z > RB_MAX_ATOMS) return fail(RB_ERR_RANGE, "rb_c51_dueling_loss_grad: atoms exceeds RB_MAX_ATOMS");
+  const size_t smem = (size_t)C51_WARPS * (3 * (Z + A * Z) + 2 * A * Z + Z) * sizeof(float);
+  if (smem > 200 * 1024) return fail(RB_ERR_RANGE, "rb_c51_dueling_loss_grad: actions * atoms too large");
   if (smem > 40 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_c51_dueling, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(RB_ERR_CUDA, cudaGetErrorString(e));
   }
   const int ctas = (B + C51_WARPS - 1) / C51_WARPS;
   { ProfScope prof_(RB_K_C51_DUELING, (cudaStream_t)stream);
-    k_c51_dueling<<<ctas, C51_WARPS * 32, smem, (cudaStream_t)stream>>>(on, tg, actions, returns, nonterminals, weights, support,
-                                                                      vmin, vmax, delta_z, gamma_n, B, A, Z, loss, dz, m_out,
-                                                                      astar_out); }
+    k_c51_dueling<<<ctas, C51_WARPS * 32, smem, (cudaStream_t)stream>>>(z_online, z_target, actions, returns, nonterminals, weights,
+                                                                      support, vmin, vmax, delta_z, gamma_n, B, A, Z, loss, dz,
+                                                                      m_out, astar_out); }
   return check_launch("rb_c51_dueling_loss_grad");
 }
 

@@ -103,6 +103,7 @@ class FusedHead:
         self.s1, self.s2 = s1.value, s2.value
         self.ncols = net.atoms * (1 + net.action_space)
         self._scratch = {}
+        self._tickets = None
 
     @staticmethod
     def supported(net):
@@ -141,24 +142,30 @@ class FusedHead:
     def _buffers(self, M, dev):
         if M not in self._scratch:
             H = self.net.hidden_size
-            self._scratch[M] = (torch.empty((self.s1, M, 2 * H), dtype=torch.float32, device=dev),
-                                torch.empty((M, 2 * H), dtype=torch.float32, device=dev),
-                                torch.empty((self.s2, M, self.ncols), dtype=torch.float32, device=dev))
+            f32 = torch.float32
+            self._scratch[M] = dict(part1=torch.empty((self.s1, M, 2 * H), dtype=f32, device=dev),
+                                    part2=torch.empty((self.s2, M, self.ncols), dtype=f32, device=dev),
+                                    h=torch.empty((M, 2 * H), dtype=f32, device=dev),
+                                    z=torch.empty((M, self.ncols), dtype=f32, device=dev))
+        if self._tickets is None:
+            self._tickets = torch.zeros(self.lib.rb_head_ticket_count(), dtype=torch.int32, device=dev)
         return self._scratch[M]
 
     def forward(self, x_lo, x_hi=None, noisy=None):
-        """x_lo [m_lo, K1] (+ x_hi [m_hi, K1]) -> (part2 [s2, M, Z(1+A)], h [M, 2H]); buffers are reused per M."""
+        """x_lo [m_lo, K1] (+ x_hi [m_hi, K1]) -> (z [M, Z(1+A)], h [M, 2H], params); buffers are reused per M."""
         m_lo = x_lo.shape[0]
         m_hi = 0 if x_hi is None else x_hi.shape[0]
-        part1, h, part2 = self._buffers(m_lo + m_hi, x_lo.device)
+        buf = self._buffers(m_lo + m_hi, x_lo.device)
         p = self.params(noisy)
-        _lib.check(self.lib.rb_head_forward(C.byref(p), _lib.ptr(x_lo), m_lo, _lib.ptr(x_hi), m_hi, _lib.ptr(part1),
-                                            _lib.ptr(h), _lib.ptr(part2), _lib.stream()))
-        return part2, h, p
+        _lib.check(self.lib.rb_head_forward(C.byref(p), _lib.ptr(x_lo), m_lo, _lib.ptr(x_hi), m_hi, _lib.ptr(buf["part1"]),
+                                            _lib.ptr(buf["part2"]), _lib.ptr(self._tickets), _lib.ptr(buf["h"]),
+                                            _lib.ptr(buf["z"]), _lib.stream()))
+        return buf["z"], buf["h"], p
 
-    def logits(self, part2, p, M):
-        q = torch.empty((M, self.net.action_space, self.net.atoms), dtype=torch.float32, device=part2.device)
-        _lib.check(self.lib.rb_head_logits(C.byref(p), _lib.ptr(part2), M, _lib.ptr(q), _lib.stream()))
+    def logits(self, z):
+        M = z.shape[0]
+        q = torch.empty((M, self.net.action_space, self.net.atoms), dtype=torch.float32, device=z.device)
+        _lib.check(self.lib.rb_head_logits(_lib.ptr(z), M, self.net.action_space, self.net.atoms, _lib.ptr(q), _lib.stream()))
         return q
 
     def backward(self, p, x, h, dz, dh_scratch, dx):
@@ -268,8 +275,8 @@ class DQN(nn.Module):
         feats = self.features(x)
         recording = torch.is_grad_enabled() and (feats.requires_grad or self.fc_h_v.weight_mu.requires_grad)
         if not recording and self.fused_ok(feats.shape[0]):
-            part2, _, p = self.head().forward(feats.contiguous())
-            return self.head().logits(part2, p, feats.shape[0])
+            z, _, _ = self.head().forward(feats.contiguous())
+            return self.head().logits(z)
         if self._eps_stale:
             self.materialise_noise()
         v = self.fc_z_v(F.relu(self.fc_h_v(feats))).view(-1, 1, self.atoms)

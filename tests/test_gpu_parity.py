@@ -510,8 +510,10 @@ def test_fused_head_forward(arch, hidden, actions, rows):
             getattr(net, mode)()
             v, a = _library_head(net, feats)
             q_ref = v.view(rows, 1, -1) + a.view(rows, actions, -1) - a.view(rows, actions, -1).mean(1, keepdim=True)
-            part2, h, p = net.head().forward(feats[:rows // 2 + 1].contiguous(), feats[rows // 2 + 1:].contiguous() if rows > 1 else None)
-            q = net.head().logits(part2, p, rows)
+            z, h, p = net.head().forward(feats[:rows // 2 + 1].contiguous(), feats[rows // 2 + 1:].contiguous() if rows > 1 else None)
+            q = net.head().logits(z)
+            np.testing.assert_allclose(cpu(z), cpu(torch.cat([v, a], 1)), rtol=1e-4, atol=2e-5)
+            assert int(net.head()._tickets.abs().sum()) == 0, "split-K tickets are self-resetting"
             np.testing.assert_allclose(cpu(q), cpu(q_ref), rtol=1e-4, atol=2e-5)
             import torch.nn.functional as F
             h_ref = torch.cat([F.relu(net.fc_h_v(feats)), F.relu(net.fc_h_a(feats))], 1)
@@ -560,7 +562,7 @@ def test_fused_head_backward(arch, hidden, actions, B):
     for p in params:
         p.grad = torch.full_like(p, 123.0)       # must be overwritten, not accumulated
     with torch.no_grad():
-        part2, h, p_ = net.head().forward(feats.detach())
+        z, h, p_ = net.head().forward(feats.detach())
         dh = torch.empty(B, 2 * hidden, device=DEV)
         dx = torch.empty(B, K1, device=DEV)
         net.head().backward(p_, feats.detach(), h[:B], dz, dh, dx)
@@ -586,16 +588,15 @@ def test_c51_dueling_entry(actions, B):
     w = t(rs.uniform(0.2, 1, B).astype(np.float32))
     support = torch.linspace(-10, 10, Z).to(DEV)
     with torch.no_grad():
-        p2_on, _, p_on = on.head().forward(x[:B].contiguous(), x[B:].contiguous())
-        p2_on = p2_on.clone()
-        p2_t, _, p_t = tg.head().forward(x[B:].contiguous())
-        q_on = on.head().logits(p2_on, p_on, 2 * B)
-        q_t = tg.head().logits(p2_t, p_t, B)
+        z_on, _, _ = on.head().forward(x[:B].contiguous(), x[B:].contiguous())
+        z_t, _, _ = tg.head().forward(x[B:].contiguous())
+        q_on = on.head().logits(z_on)
+        q_t = tg.head().logits(z_t)
         m1 = torch.empty(B, Z, device=DEV); m2 = torch.empty(B, Z, device=DEV)
         a1 = torch.empty(B, dtype=torch.int64, device=DEV); a2 = torch.empty(B, dtype=torch.int64, device=DEV)
         loss_ref, gq = c51_loss_grad(q_on[:B].contiguous(), q_on[B:].contiguous(), q_t, acts, rets, nont, w, support, -10.0, 10.0,
                                      0.4, 0.99 ** 3, m_out=m1, astar_out=a1)
-        loss, dz = c51_dueling_loss_grad(p_on, p2_on, p_t, p2_t, acts, rets, nont, w, support, -10.0, 10.0, 0.4, 0.99 ** 3,
+        loss, dz = c51_dueling_loss_grad(z_on, z_t, A, Z, acts, rets, nont, w, support, -10.0, 10.0, 0.4, 0.99 ** 3,
                                          m_out=m2, astar_out=a2)
     assert torch.equal(a1, a2)
     np.testing.assert_allclose(cpu(m2), cpu(m1), rtol=0, atol=1e-6)
