@@ -206,25 +206,46 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-#pragma unroll
-    for (int i = 0; i < TM; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-    for (int sp = 0; sp < S; ++sp) {
-#pragma unroll
-      for (int i = 0; i < TM; ++i) {
-        const int m = m0 + ty * TM + i;
-        if (m >= M) continue;
-        const float* src = part + ((size_t)sp * M + m) * ncols + colbase;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int n = n0 + tx * 4 + j;
-          if (n < Ns) acc[i][j] += __ldcg(src + n);
+    // ---- cooperative, vectorised reduction of the S partial tiles + epilogue (bias, ReLU for layer 1) ----
+    const float* __restrict__ bmu_t = (LAYER == 1) ? d.b1_mu[s] : d.b2_mu[s];
+    const float* __restrict__ bsg_t = (LAYER == 1) ? d.b1_sig[s] : d.b2_sig[s];
+    const size_t slice = (size_t)M * ncols;
+    if (LAYER == 1) {  // ncols = 2H and colbase + n0 are multiples of 4: float4 path
+      for (int idx = tid; idx < MT * (NT / 4); idx += HT) {
+        const int row = idx / (NT / 4), c = (idx % (NT / 4)) * 4, m = m0 + row, n = n0 + c;
+        if (m >= M || n >= Ns) continue;
+        const float* src = part + (size_t)m * ncols + colbase + n;
+        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 5
+        for (int sp = 0; sp < S; ++sp) {
+          const float4 pv = __ldcg(reinterpret_cast<const float4*>(src + sp * slice));
+          a4.x += pv.x; a4.y += pv.y; a4.z += pv.z; a4.w += pv.w;
         }
+        float4 bv = __ldg(reinterpret_cast<const float4*>(bmu_t + n));
+        if (eo) {
+          const float4 bs = __ldg(reinterpret_cast<const float4*>(bsg_t + n));
+          const float4 e4 = __ldg(reinterpret_cast<const float4*>(eo + n));
+          bv.x = fmaf(bs.x, e4.x, bv.x); bv.y = fmaf(bs.y, e4.y, bv.y); bv.z = fmaf(bs.z, e4.z, bv.z); bv.w = fmaf(bs.w, e4.w, bv.w);
+        }
+        a4.x = fmaxf(a4.x + bv.x, 0.f); a4.y = fmaxf(a4.y + bv.y, 0.f); a4.z = fmaxf(a4.z + bv.z, 0.f); a4.w = fmaxf(a4.w + bv.w, 0.f);
+        *reinterpret_cast<float4*>(out + (size_t)m * ncols + colbase + n) = a4;
+      }
+    } else {
+      for (int idx = tid; idx < MT * NT; idx += HT) {
+        const int row = idx / NT, c = idx % NT, m = m0 + row, n = n0 + c;
+        if (m >= M || n >= Ns) continue;
+        const float* src = part + (size_t)m * ncols + colbase + n;
+        float a1 = 0.0f;
+#pragma unroll 4
+        for (int sp = 0; sp < S; ++sp) a1 += __ldcg(src + sp * slice);
+        float bv = __ldg(bmu_t + n);
+        if (eo) bv = fmaf(__ldg(bsg_t + n), __ldg(eo + n), bv);
+        out[(size_t)m * ncols + colbase + n] = a1 + bv;
       }
     }
+    return;
   }
-  // ---- epilogue: composed bias (+ ReLU for layer 1) ----
+  // ---- no split (S == 1): epilogue straight from the accumulators ----
   const float* __restrict__ bmu = (LAYER == 1) ? d.b1_mu[s] : d.b2_mu[s];
   const float* __restrict__ bsg = (LAYER == 1) ? d.b1_sig[s] : d.b2_sig[s];
   float bias[4];

@@ -132,6 +132,80 @@ k_tree_update(float* tree, int64_t tree_start, int64_t size, const int64_t* __re
   }
 }
 
+// Fast path for B <= 32 (the learner's batch): ONE warp, no barriers.  Every lane first fetches all L siblings
+// of its leaf-to-root path in one batch of independent loads (they are untouched by this kernel unless another
+// lane's path owns them), then the warp walks the levels in registers: lanes that share a parent find each other
+// with __match_any_sync, take the sibling value from the partner lane when the sibling is itself on an updated
+// path (else from the prefetched value), and the lowest lane of each group writes the node.  L dependent global
+// round trips (one per level, with a CTA barrier each) become one.
+constexpr int UPD_MAX_LEVELS = 40;
+
+__global__ void __launch_bounds__(32, 1)
+k_tree_update_warp(float* tree, int64_t tree_start, int64_t size, const int64_t* __restrict__ tree_idx,
+                   const float* __restrict__ raw, float omega, int omega_is_applied, int B, float* running_max,
+                   int32_t* status) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x;
+  const int64_t len = tree_start + size;
+  const int L = tree_depth(tree_start);
+  int64_t node = -1;
+  float val = 0.0f;
+  if (lane < B) {
+    node = tree_idx[lane];
+    float r = raw[lane];
+    if (omega_is_applied) val = r;
+    else if (omega == 0.5f) val = __fsqrt_rn(r);
+    else if (omega == 1.0f) val = r;
+    else val = (float)pow((double)r, (double)omega);
+    if (node < tree_start || node >= len) {
+      if (status) atomicExch(status, 1);
+      node = -1;
+    }
+  }
+  const bool active = node >= 0;
+  float vmax = active ? val : -CUDART_INF_F;
+  vmax = warp_max(vmax);
+  // duplicates: the highest lane (= last in index order) wins, memory.py:45 fancy assignment
+  {
+    const long long key = active ? (long long)node : -(long long)(lane + 1);
+    const unsigned grp = __match_any_sync(full, key);
+    const int winner = 31 - __clz(grp);
+    val = __shfl_sync(full, val, winner);
+  }
+  // prefetch the siblings along the path (independent loads)
+  float sib[UPD_MAX_LEVELS];
+#pragma unroll
+  for (int l = 0; l < UPD_MAX_LEVELS; ++l) {
+    sib[l] = 0.0f;
+    if (l < L && active) {
+      const int64_t nl = ((node + 1) >> l) - 1;           // ancestor l levels up
+      const int64_t sn = (nl & 1) ? nl + 1 : nl - 1;      // odd index = left child
+      sib[l] = __ldcg(tree + sn);
+    }
+  }
+  {
+    const long long key = active ? (long long)node : -(long long)(lane + 1);
+    const unsigned grp = __match_any_sync(full, key);
+    if (active && lane == __ffs(grp) - 1) __stcg(tree + node, val);
+  }
+#pragma unroll
+  for (int l = 0; l < UPD_MAX_LEVELS; ++l) {
+    if (l < L) {
+      const int64_t parent = active ? ((node - 1) >> 1) : -(int64_t)(lane + 1);
+      const bool is_left = active && (node & 1);
+      const unsigned grp = __match_any_sync(full, (long long)parent);
+      const unsigned lefts = __ballot_sync(full, is_left);
+      const unsigned other = grp & (is_left ? ~lefts : lefts);
+      const float partner = __shfl_sync(full, val, other ? __ffs(other) - 1 : lane);
+      const float sv = other ? partner : sib[l];
+      val = __fadd_rn(val, sv);                            // fl32(left + right); float addition commutes
+      node = parent;
+      if (active && lane == __ffs(grp) - 1) __stcg(tree + node, val);
+    }
+  }
+  if (lane == 0 && vmax > *running_max) *running_max = vmax;   // memory.py:47-48
+}
+
 // ================================================================================================
 // Tree descent shared by K1 (sample) and rb_tree_find.
 // ================================================================================================
@@ -251,6 +325,7 @@ k_tree_sample(const float* __restrict__ tree, int64_t tree_start, int64_t size, 
   __shared__ float s_top[TOP_NODES];
   __shared__ int s_valid;
   __shared__ float s_red[32];
+  __shared__ float s_prob[SAMPLE_THREADS];   // leaf values of the first SAMPLE_THREADS samples (kept on chip for the weights)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   const int64_t len = tree_start + size;
   const int L = tree_depth(tree_start);
@@ -284,6 +359,7 @@ k_tree_sample(const float* __restrict__ tree, int64_t tree_start, int64_t size, 
       if (lane == 0) {
         int64_t di = r.node - tree_start;
         probs[k] = r.prob;
+        if (k < SAMPLE_THREADS) s_prob[k] = r.prob;
         data_idx[k] = di;
         tree_idx[k] = r.node;
         bool ok = (pymod(head - di, size) > (int64_t)n) && (pymod(di - head, size) >= (int64_t)history) &&
@@ -304,17 +380,18 @@ k_tree_sample(const float* __restrict__ tree, int64_t tree_start, int64_t size, 
   const float nb = -b;
   const float count = (float)(full ? size : head);
   float wmax = -CUDART_INF_F;
+  float w_first = 0.0f;   // weight of sample k = tid (kept in a register), later samples go through global memory
   for (int k = tid; k < B; k += blockDim.x) {
-    float p = __fdiv_rn(probs[k], p_total);
+    float p = __fdiv_rn(k < SAMPLE_THREADS ? s_prob[k] : probs[k], p_total);
     float w = (float)pow((double)__fmul_rn(count, p), (double)nb);
-    weights[k] = w;
+    if (k == tid) w_first = w; else weights[k] = w;
     wmax = fmaxf(wmax, w);
   }
   wmax = warp_max(wmax);
   if (lane == 0) s_red[warp] = wmax;
   __syncthreads();
   wmax = warp_max(s_red[lane]);
-  for (int k = tid; k < B; k += blockDim.x) weights[k] = __fdiv_rn(weights[k], wmax);
+  for (int k = tid; k < B; k += blockDim.x) weights[k] = __fdiv_rn(k == tid ? w_first : weights[k], wmax);
   if (tid == 0) {
     status[0] = ok_batch ? 1 : 0;
     status[1] = attempt;
@@ -372,6 +449,13 @@ k_gather(const uint8_t* __restrict__ frames, const int32_t* __restrict__ timeste
   // used-slot -> window slot: slots [0,H) feed `states`, [n,n+H) feed `next_states`
   const int s = (n >= history && used >= history) ? n + (used - history) : used;
   const int64_t idx = data_idx[b];
+  const int64_t pos = pymod(idx - (history - 1) + s, size);
+  const int per = (FRAME_VEC + split - 1) / split;
+  const int v0 = part * per, v1 = min(FRAME_VEC, v0 + per);
+  // issue the (rarely discarded) frame load first so it overlaps the timestep loads that decide the blanking
+  const uint4* src = reinterpret_cast<const uint4*>(frames + (size_t)pos * RB_FRAME_BYTES);
+  uint4 pre = make_uint4(0, 0, 0, 0);
+  if (v0 + (int)threadIdx.x < v1) pre = __ldg(src + v0 + threadIdx.x);
   if (threadIdx.x < 32) {
     uint64_t f = window_first_bits(timestep, size, idx, history, W);
     if (threadIdx.x == 0) s_first = f;
@@ -379,17 +463,13 @@ k_gather(const uint8_t* __restrict__ frames, const int32_t* __restrict__ timeste
   __syncthreads();
   const uint64_t first = s_first;
   const bool blank = slot_blank(first, s, history);
-  const int64_t pos = pymod(idx - (history - 1) + s, size);
 
   float4* dst_s = (s < history) ? reinterpret_cast<float4*>(states + ((size_t)b * history + s) * RB_FRAME_BYTES) : nullptr;
   float4* dst_n = (s >= n && s < n + history)
                       ? reinterpret_cast<float4*>(next_states + ((size_t)b * history + (s - n)) * RB_FRAME_BYTES)
                       : nullptr;
-  const uint4* src = reinterpret_cast<const uint4*>(frames + (size_t)pos * RB_FRAME_BYTES);
-  const int per = (FRAME_VEC + split - 1) / split;
-  const int v0 = part * per, v1 = min(FRAME_VEC, v0 + per);
   for (int v = v0 + threadIdx.x; v < v1; v += GATHER_THREADS) {
-    uint4 q = blank ? make_uint4(0, 0, 0, 0) : __ldg(src + v);
+    uint4 q = blank ? make_uint4(0, 0, 0, 0) : (v == v0 + (int)threadIdx.x ? pre : __ldg(src + v));
     float4 a = u8x4_to_unit(q.x), bq = u8x4_to_unit(q.y), c = u8x4_to_unit(q.z), d = u8x4_to_unit(q.w);
     if (dst_s) {
       __stcs(dst_s + 4 * v + 0, a); __stcs(dst_s + 4 * v + 1, bq); __stcs(dst_s + 4 * v + 2, c); __stcs(dst_s + 4 * v + 3, d);
@@ -610,6 +690,17 @@ __device__ __forceinline__ void c51_core(C51Scratch& sc, int lane, int i, int B,
   __syncwarp();
 
   // ---- agent.py:89-92: m, deterministic gather in index_add_ order ----
+  // Tz is non-decreasing in the atom index (support increasing, scale >= 0) and u == l + 1 after the fix-ups, so
+  // the source atoms feeding target k on the l side form the contiguous run {j : l[j] == k} and on the u side the
+  // run {j : l[j] == k - 1}: two binary searches replace the 2*Z-long scans.  The additions still happen in atom
+  // order, l side first (bit-identical to the scan).  Odd inputs (NaN, decreasing support) take the full scan.
+  bool mono = true;
+#pragma unroll
+  for (int r = 0; r < C51_R; ++r) {
+    const int z = lane + 32 * r;
+    if (z < Z) mono = mono && (sc.u[z] == sc.l[z] + 1) && (z + 1 >= Z || sc.l[z] <= sc.l[z + 1]);
+  }
+  mono = __all_sync(0xffffffffu, mono);
   float m[C51_R];
   float ce = 0.0f, msum = 0.0f;
 #pragma unroll
@@ -617,10 +708,25 @@ __device__ __forceinline__ void c51_core(C51Scratch& sc, int lane, int i, int B,
     const int k = lane + 32 * r;
     float acc = 0.0f;
     if (k < Z) {
-      for (int j = 0; j < Z; ++j)
-        if (sc.l[j] == k) acc = __fadd_rn(acc, __fmul_rn(sc.pt[j], __fsub_rn((float)sc.u[j], sc.b[j])));
-      for (int j = 0; j < Z; ++j)
-        if (sc.u[j] == k) acc = __fadd_rn(acc, __fmul_rn(sc.pt[j], __fsub_rn(sc.b[j], (float)sc.l[j])));
+      if (mono) {
+        int lo = 0, hi = Z;              // first j with l[j] >= k - 1
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (sc.l[mid] < k - 1) lo = mid + 1; else hi = mid;
+        }
+        int j = lo;
+        const int ju = j;                // start of the u-side run (l == k - 1)
+        while (j < Z && sc.l[j] == k - 1) ++j;
+        for (int jj = j; jj < Z && sc.l[jj] == k; ++jj)
+          acc = __fadd_rn(acc, __fmul_rn(sc.pt[jj], __fsub_rn((float)sc.u[jj], sc.b[jj])));
+        for (int jj = ju; jj < j; ++jj)
+          acc = __fadd_rn(acc, __fmul_rn(sc.pt[jj], __fsub_rn(sc.b[jj], (float)sc.l[jj])));
+      } else {
+        for (int j = 0; j < Z; ++j)
+          if (sc.l[j] == k) acc = __fadd_rn(acc, __fmul_rn(sc.pt[j], __fsub_rn((float)sc.u[j], sc.b[j])));
+        for (int j = 0; j < Z; ++j)
+          if (sc.u[j] == k) acc = __fadd_rn(acc, __fmul_rn(sc.pt[j], __fsub_rn(sc.b[j], (float)sc.l[j])));
+      }
       if (m_out) m_out[(size_t)i * Z + k] = acc;
     }
     m[r] = acc;
@@ -869,13 +975,26 @@ k_sqnorm(const float* __restrict__ grad, int64_t P, float grad_scale, double* __
   }
 }
 
+// sqrt / reciprocal through the SFU approximations (<= 2 ulp): the kernel was partly instruction bound on the
+// IEEE div/sqrt sequences (r01 ncu: SM throughput 55 %), and the update tolerates 1e-6 relative error.
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float coef, float b1, float b2,
-                                         float step_size, float bc2_sqrt, float eps) {
+                                         float step_size, float inv_bc2_sqrt, float eps) {
   g = g * coef;
-  m = m + (g - m) * (1.0f - b1);                 // exp_avg.lerp_(grad, 1 - beta1)
-  v = v * b2 + (1.0f - b2) * g * g;              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-  float denom = sqrtf(v) / bc2_sqrt + eps;
-  p = p - step_size * (m / denom);               // param.addcdiv_(exp_avg, denom, value=-step_size)
+  m = fmaf(g - m, 1.0f - b1, m);                 // exp_avg.lerp_(grad, 1 - beta1)
+  v = fmaf(v, b2, (1.0f - b2) * g * g);          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  const float denom = fmaf(fast_sqrt(v), inv_bc2_sqrt, eps);
+  p = fmaf(-step_size * m, fast_rcp(denom), p);  // param.addcdiv_(exp_avg, denom, value=-step_size)
 }
 
 __global__ void __launch_bounds__(ADAM_THREADS)
@@ -906,7 +1025,7 @@ k_clip_adam(float* __restrict__ param, const float* __restrict__ grad, float* __
   const double bc1 = 1.0 - pow((double)b1, (double)step);
   const double bc2 = 1.0 - pow((double)b2, (double)step);
   const float step_size = (float)((double)lr / bc1);
-  const float bc2_sqrt = (float)sqrt(bc2);
+  const float bc2_sqrt = (float)(1.0 / sqrt(bc2));  // passed to adam_one as the reciprocal
 
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -981,8 +1100,12 @@ int rb_tree_update(float* tree, int64_t tree_start, int64_t size, const int64_t*
   if (!tree || !tree_idx || !raw_priority || !running_max) return fail(RB_ERR_INVAL, "rb_tree_update: null pointer");
   if (B <= 0 || size <= 0 || (size & 1)) return fail(RB_ERR_INVAL, "rb_tree_update: B > 0 and an even size are required");
   { ProfScope prof_(RB_K_TREE_UPDATE, (cudaStream_t)stream);
-    k_tree_update<<<1, UPD_THREADS, 0, (cudaStream_t)stream>>>(tree, tree_start, size, tree_idx, raw_priority, omega,
-                                                             omega_is_applied, B, running_max, status); }
+    if (B <= 32 && tree_depth(tree_start) <= UPD_MAX_LEVELS)
+      k_tree_update_warp<<<1, 32, 0, (cudaStream_t)stream>>>(tree, tree_start, size, tree_idx, raw_priority, omega,
+                                                            omega_is_applied, B, running_max, status);
+    else
+      k_tree_update<<<1, UPD_THREADS, 0, (cudaStream_t)stream>>>(tree, tree_start, size, tree_idx, raw_priority, omega,
+                                                               omega_is_applied, B, running_max, status); }
   return check_launch("rb_tree_update");
 }
 
@@ -1017,7 +1140,7 @@ int rb_tree_sample(const float* tree, int64_t tree_start, int64_t size, const in
 static int gather_split(int ctas_without_split) {
   // aim for >= 4 CTAs per SM (148 SMs) so small batches still cover the machine; a frame is 441 x 16 B
   int split = 1;
-  while (split < 8 && ctas_without_split * split < 148 * 4) split *= 2;
+  while (split < 2 && ctas_without_split * split < 148 * 2) split *= 2;  // 221 of 256 threads busy per CTA at split 2
   return split;
 }
 
