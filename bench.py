@@ -214,6 +214,8 @@ def workload_config(name, cfg, gpus):
 def algorithmic_bytes(cfg, P, noisy_elems):
     """SURVEY.md 8(d) per-launch algorithmic bytes of each hand-written kernel."""
     B, n, H, F, Z, A = cfg["B"], cfg["n"], 4, 7056, 51, ACTIONS
+    K1 = 3136 if cfg["arch"] == "canonical" else 576
+    head = dict(K1=K1, H=cfg["hidden"], N2=Z * (1 + A), w1=2 * cfg["hidden"] * K1, w2=Z * (1 + A) * cfg["hidden"])
     cap = cfg["cap"]
     L = (cap - 1).bit_length()
     return {
@@ -225,6 +227,14 @@ def algorithmic_bytes(cfg, P, noisy_elems):
         "sqnorm": P * 4,                            # read grad
         "clip_adam": 7 * P * 4,                     # read p,g,m,v ; write p,m,v
         "append": F * 4 + F + 13 + L * 8,
+        # fused head (canonical: K1 3136, H 512): weights mu+sigma read once per launch + activations in/out
+        "head_fc1": head["w1"] * 2 * 4 + 2 * B * head["K1"] * 4 + 2 * B * 2 * head["H"] * 4,            # online pass (2B rows)
+        "head_fc2": head["w2"] * 2 * 4 + 2 * B * 2 * head["H"] * 4 + 2 * B * head["N2"] * 4,
+        "head_bwd1": head["w1"] * 2 * 4 * 2 + B * (head["K1"] + 2 * head["H"]) * 4 + B * head["K1"] * 4,  # read mu,sigma; write both grads
+        "head_dh": head["w2"] * 2 * 4 + B * (head["N2"] + 2 * 2 * head["H"]) * 4,
+        "head_wgrad2": head["w2"] * 2 * 4 + B * (head["N2"] + 2 * head["H"]) * 4,
+        "c51_dueling": 3 * B * head["N2"] * 4 + B * 20 + Z * 4 + B * head["N2"] * 4 + B * 4,
+        "noise_factors": (head["K1"] * 2 + head["H"] * 4 + head["N2"]) * 4,
     }
 
 
@@ -355,7 +365,8 @@ def ours(opts, cfg, rank, world, local):
     P = agent.optimiser.numel
     noisy = sum(m.weight_epsilon.numel() + m.bias_epsilon.numel() for m in agent.online_net.noisy_layers())
     alg = algorithmic_bytes(cfg, P, noisy)
-    launches_per_step = {"noisy_resample": 2, "tree_sample": 1, "gather": 1, "c51": 1, "sqnorm": 1, "clip_adam": 1, "tree_update": 1}
+    launches_per_step = {"noise_factors": 2, "tree_sample": 1, "gather": 1, "head_fc1": 2, "head_fc2": 2, "c51_dueling": 1,
+                         "head_wgrad2": 1, "head_dh": 1, "head_bwd1": 1, "sqnorm": 1, "clip_adam": 1, "tree_update": 1}
     kernels = {}
     for name, (cnt, us) in kt.result.items():
         if name in alg:
@@ -373,6 +384,7 @@ def ours(opts, cfg, rank, world, local):
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": d["bytes"], "us_per_launch": d["us"],
                 "timing": "CUDA events around each launch on its stream, eager (non-graph) replay of the same step",
                 "kernels": kernels,
+                "all_kernel_us": {k: round(v[1], 2) for k, v in kt.result.items()},
                 "own_kernel_us_per_step": round(sum(step_kernel_us.values()), 1)}
 
     total_updates = K * world
@@ -386,9 +398,10 @@ def ours(opts, cfg, rank, world, local):
                     "h2d_bytes_per_step": REPLAY_FREQUENCY * 84 * 84 * 4, "d2h_bytes_per_step": B * 4,
                     "what": f"per step: {REPLAY_FREQUENCY} x mem.append(frame from pinned host memory) + dqn.reset_noise() + dqn.learn(mem) + "
                             "per-sample loss copied to the host"},
-            # our kernels launched in the timed `value` region: per step 2 x (k_noisy_resample + k_bump_counter) + k_tree_sample
-            # + k_gather + k_c51 + k_sqnorm + k_clip_adam + k_bump_step + k_tree_update = 11
-            "gpu_launches": K * 11,
+            # our kernels launched in the timed `value` region, per step: 2 k_noise_factors, k_tree_sample, k_gather,
+            # 2 x (k_head_fc<.,1> + k_head_fc<.,2>), k_c51_dueling, k_head_wgrad2, k_head_dh, k_head_bwd1, k_sqnorm, k_clip_adam,
+            # k_bump_step, k_tree_update = 16
+            "gpu_launches": K * 16,
             "clocks": clocks, "roofline": roofline}
     if world == 1 and not opts.no_cpu_baseline:
         ups, dt, threads, n_cpu = run_cpu_port(cfg, opts.cpu_updates, 3, with_appends=True, budget_s=25)

@@ -164,6 +164,7 @@ class Agent:
 
         self.use_cuda_graph = bool(getattr(args, "cuda_graph", True))
         self.use_fused_head = bool(getattr(args, "fused_head", True))
+        self._streams = None
         self._graph = None
         self._graph_key = None
         self._ws = None
@@ -202,21 +203,46 @@ class Agent:
         on = self.online_net
         return self.use_fused_head and B <= 32 and on.training and on.fused_ok(2 * B) and self.target_net.fused_ok(B)
 
+    def _side_streams(self):
+        if self._streams is None:
+            self._streams = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
+        return self._streams
+
     def _update_fused(self, batch, target_noise=None):
-        """agent.py:66-98 with the fused head: torch only runs the conv bodies (forward x3, backward x1)."""
+        """agent.py:66-98 with the fused head: torch only runs the conv bodies (forward x3, backward x1).
+        The three network passes are independent until the loss, and every conv kernel of this size leaves most of the
+        148 SMs idle, so they run as three concurrent branches (fork/join with events; inside the captured CUDA graph
+        they become parallel branches): online(s) with autograd on the caller's stream, online(s') and the whole
+        target pass (noise draw, convs, head) on two side streams."""
         idxs, states, actions, returns, next_states, nonterminals, weights = batch
         on, tg = self.online_net, self.target_net
         B = states.shape[0]
-        x_s = on.features(states)                      # autograd graph: convs only
-        with torch.no_grad():
-            x_ns = on.features(next_states)
-            xs_d = x_s.detach()
-            z_on, h_on, p_on = on.head().forward(xs_d, x_ns)              # rows [0,B) = s, [B,2B) = s'
+        main = torch.cuda.current_stream(self.device)
+        s_ns, s_tg = self._side_streams()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        with torch.cuda.stream(s_tg), torch.no_grad():
+            s_tg.wait_event(fork)
             if target_noise is None:
                 tg.reset_noise()                                            # agent.py:74
             else:
                 tg.reset_noise(*target_noise)
-            z_t, _, _ = tg.head().forward(tg.features(next_states))
+            x_t = tg.features_nograd(next_states)
+            z_t, _, _ = tg.head().forward(x_t)
+            done_tg = torch.cuda.Event()
+            done_tg.record(s_tg)
+        with torch.cuda.stream(s_ns), torch.no_grad():
+            s_ns.wait_event(fork)
+            x_ns = on.features_nograd(next_states)
+            done_ns = torch.cuda.Event()
+            done_ns.record(s_ns)
+        x_s = on.features(states)                      # autograd graph: convs only
+        with torch.no_grad():
+            xs_d = x_s.detach()
+            main.wait_event(done_ns)
+            x_ns.record_stream(main)
+            z_on, h_on, p_on = on.head().forward(xs_d, x_ns)              # rows [0,B) = s, [B,2B) = s'
+            main.wait_event(done_tg)
             loss, dz = c51_dueling_loss_grad(z_on, z_t, self.action_space, self.atoms, actions, returns, nonterminals, weights,
                                              self.support, self.Vmin, self.Vmax, self.delta_z, self.discount ** self.n)
             self.optimiser.zero_conv_grad()

@@ -270,6 +270,16 @@ class DQN(nn.Module):
     def features(self, x):
         return self.convs(x).view(-1, self.conv_output_size)
 
+    def features_nograd(self, x):
+        """Inference-only conv body: cuDNN's fused conv + bias + ReLU (one launch per layer instead of three).
+        Same arithmetic as features() (bit-identical outputs on B200 [probe tools/conv_probe.py])."""
+        if not (x.is_cuda and torch.backends.cudnn.enabled):
+            return self.features(x)
+        for m in self.convs:
+            if isinstance(m, nn.Conv2d):
+                x = torch.cudnn_convolution_relu(x, m.weight, m.bias, m.stride, m.padding, m.dilation, m.groups)
+        return x.view(-1, self.conv_output_size)
+
     def logits(self, x):
         """Pre-softmax q [B, A, Z] (model.py:69-75)."""
         feats = self.features(x)
