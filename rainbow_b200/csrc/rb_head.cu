@@ -33,6 +33,7 @@ constexpr int HT = 128;  // threads per CTA
 constexpr int NT = 64;   // output-column tile
 constexpr int KT = 32;   // reduction tile
 constexpr int LDB = NT + 4;
+constexpr int FC_T = 256;  // threads of the forward GEMM kernels
 
 struct HeadDesc {  // device pointers; stream 0 = value, 1 = advantage.  Noise pointers may be null (eval mode).
   const float* w1_mu[2]; const float* w1_sig[2]; const float* b1_mu[2]; const float* b1_sig[2];
@@ -70,10 +71,10 @@ __device__ __forceinline__ int col2_of(const HeadDesc& d, int s) { return s == 0
 // bias (composed b_mu + b_sigma*eps_out) / ReLU epilogue and writes the final tile.
 // ------------------------------------------------------------------------------------------------
 template <int MT, int LAYER>
-__global__ void __launch_bounds__(HT)
+__global__ void __launch_bounds__(FC_T, 2)
 k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, int m_lo, const float* __restrict__ x_hi,
           int M, float* __restrict__ part, float* __restrict__ out, int* __restrict__ tickets, int kslice) {
-  constexpr int TM = MT / 8;
+  constexpr int TM = MT / 16;  // 256 threads = 16 (m groups) x 16 (n groups of 4): micro tile TM x 4
   constexpr int LDA = MT + 4;
   __shared__ __align__(16) float As[KT][LDA];
   __shared__ __align__(16) float Bs[KT][LDB];
@@ -100,14 +101,14 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
-  constexpr int A_PER = MT * (KT / 4) / HT;  // float4 per thread for the A tile (2 or 4)
-  constexpr int B_PER = NT * (KT / 4) / HT;  // 4
+  constexpr int A_PER = MT * (KT / 4) / FC_T;  // float4 per thread for the A tile (1 or 2)
+  constexpr int B_PER = NT * (KT / 4) / FC_T;  // 2
   float4 ra[A_PER], rmu[B_PER], rsg[B_PER];
 
   auto load_tile = [&](int k0) {
 #pragma unroll
     for (int j = 0; j < A_PER; ++j) {
-      const int idx = tid + j * HT, row = idx >> 3, k = k0 + (idx & 7) * 4, m = m0 + row;
+      const int idx = tid + j * FC_T, row = idx >> 3, k = k0 + (idx & 7) * 4, m = m0 + row;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (m < M && k < k_end) {
         if (LAYER == 1) {
@@ -121,7 +122,7 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
     }
 #pragma unroll
     for (int j = 0; j < B_PER; ++j) {
-      const int idx = tid + j * HT, row = idx >> 3, k = k0 + (idx & 7) * 4, n = n0 + row;
+      const int idx = tid + j * FC_T, row = idx >> 3, k = k0 + (idx & 7) * 4, n = n0 + row;
       float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = m4;
       if (n < Ns && k < k_end) {
         m4 = __ldg(reinterpret_cast<const float4*>(mu + (size_t)n * K + k));
@@ -134,12 +135,12 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
   auto store_tile = [&](int k0) {
 #pragma unroll
     for (int j = 0; j < A_PER; ++j) {
-      const int idx = tid + j * HT, row = idx >> 3, kk = (idx & 7) * 4;
+      const int idx = tid + j * FC_T, row = idx >> 3, kk = (idx & 7) * 4;
       As[kk + 0][row] = ra[j].x; As[kk + 1][row] = ra[j].y; As[kk + 2][row] = ra[j].z; As[kk + 3][row] = ra[j].w;
     }
 #pragma unroll
     for (int j = 0; j < B_PER; ++j) {
-      const int idx = tid + j * HT, row = idx >> 3, kk = (idx & 7) * 4, k = k0 + kk, n = n0 + row;
+      const int idx = tid + j * FC_T, row = idx >> 3, kk = (idx & 7) * 4, k = k0 + kk, n = n0 + row;
       float4 w = rmu[j];
       if (ei && n < Ns && k < k_end) {  // compose W = mu + sigma * (eps_out[n] * eps_in[k])   (model.py:39,43)
         const float e = __ldg(eo + n);
@@ -162,10 +163,12 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
 #pragma unroll
     for (int kk = 0; kk < KT; ++kk) {
       float a[TM];
-#pragma unroll
-      for (int i = 0; i < TM; i += 4) {
-        float4 t = *reinterpret_cast<const float4*>(&As[kk][ty * TM + i]);
-        a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+      if (TM == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&As[kk][ty * TM]);
+        a[0] = t.x; a[1] = t.y; a[TM - 2] = t.z; a[TM - 1] = t.w;
+      } else {
+        const float2 t = *reinterpret_cast<const float2*>(&As[kk][ty * TM]);
+        a[0] = t.x; a[1] = t.y;
       }
       const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
 #pragma unroll
@@ -211,7 +214,7 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
     const float* __restrict__ bsg_t = (LAYER == 1) ? d.b1_sig[s] : d.b2_sig[s];
     const size_t slice = (size_t)M * ncols;
     if (LAYER == 1) {  // ncols = 2H and colbase + n0 are multiples of 4: float4 path
-      for (int idx = tid; idx < MT * (NT / 4); idx += HT) {
+      for (int idx = tid; idx < MT * (NT / 4); idx += FC_T) {
         const int row = idx / (NT / 4), c = (idx % (NT / 4)) * 4, m = m0 + row, n = n0 + c;
         if (m >= M || n >= Ns) continue;
         const float* src = part + (size_t)m * ncols + colbase + n;
@@ -231,7 +234,7 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
         *reinterpret_cast<float4*>(out + (size_t)m * ncols + colbase + n) = a4;
       }
     } else {
-      for (int idx = tid; idx < MT * NT; idx += HT) {
+      for (int idx = tid; idx < MT * NT; idx += FC_T) {
         const int row = idx / NT, c = idx % NT, m = m0 + row, n = n0 + c;
         if (m >= M || n >= Ns) continue;
         const float* src = part + (size_t)m * ncols + colbase + n;
@@ -380,8 +383,6 @@ k_head_dh(const __grid_constant__ HeadDesc d, const float* __restrict__ dz, cons
   const int Ns = n2_of(d, s), colbase = col2_of(d, s), ncols = d.Z + d.A * d.Z;
   const float* ei = d.ei2[s];
   const float* eo = d.eo2[s];
-  float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ei) e4 = __ldg(reinterpret_cast<const float4*>(ei + k0 + tk * 4));
   float acc[2][4];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -395,21 +396,44 @@ k_head_dh(const __grid_constant__ HeadDesc d, const float* __restrict__ dz, cons
     cp_async16(Wm + (size_t)o * DH_LD + k4, d.w2_mu[s] + (size_t)(ob + o) * d.H + k0 + k4);
     if (ei) cp_async16(Wsg + (size_t)o * DH_LD + k4, d.w2_sig[s] + (size_t)(ob + o) * d.H + k0 + k4);
   }
-  for (int idx = tid; idx < 32 * nb; idx += HT) {
-    const int m = idx / nb, o = idx - m * nb;
-    Dt[(size_t)o * 36 + m] = (m < B) ? __ldg(dz + (size_t)m * ncols + colbase + ob + o) : 0.0f;
+  for (int base = tid; base < 32 * nb; base += HT * 8) {  // dz chunk, transposed; 8 loads in flight per thread
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * HT;
+      v[u] = 0.0f;
+      if (idx < 32 * nb) {
+        const int m = idx / nb, o = idx - m * nb;
+        if (m < B) v[u] = __ldg(dz + (size_t)m * ncols + colbase + ob + o);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * HT;
+      if (idx < 32 * nb) {
+        const int m = idx / nb, o = idx - m * nb;
+        Dt[(size_t)o * 36 + m] = v[u];
+      }
+    }
   }
   cp_async_wait_all();
   __syncthreads();
-#pragma unroll 4
-  for (int o = 0; o < nb; ++o) {
-    float4 w = *reinterpret_cast<const float4*>(Wm + (size_t)o * DH_LD + tk * 4);
-    if (ei) {
-      const float4 sg = *reinterpret_cast<const float4*>(Wsg + (size_t)o * DH_LD + tk * 4);
+  if (ei) {  // compose W2 = mu + sigma * (eps_out[o] * eps_in[k]) in place (one vectorised pass, all threads)
+    for (int idx = tid; idx < nb * (DH_K / 4); idx += HT) {
+      const int o = idx >> 3, k4 = (idx & 7) * 4;
+      float4 w = *reinterpret_cast<const float4*>(Wm + (size_t)o * DH_LD + k4);
+      const float4 sg = *reinterpret_cast<const float4*>(Wsg + (size_t)o * DH_LD + k4);
+      const float4 ek = __ldg(reinterpret_cast<const float4*>(ei + k0 + k4));
       const float e = __ldg(eo + ob + o);
-      w.x = fmaf(sg.x, e * e4.x, w.x); w.y = fmaf(sg.y, e * e4.y, w.y);
-      w.z = fmaf(sg.z, e * e4.z, w.z); w.w = fmaf(sg.w, e * e4.w, w.w);
+      w.x = fmaf(sg.x, e * ek.x, w.x); w.y = fmaf(sg.y, e * ek.y, w.y);
+      w.z = fmaf(sg.z, e * ek.z, w.z); w.w = fmaf(sg.w, e * ek.w, w.w);
+      *reinterpret_cast<float4*>(Wm + (size_t)o * DH_LD + k4) = w;
     }
+    __syncthreads();
+  }
+#pragma unroll 8
+  for (int o = 0; o < nb; ++o) {
+    const float4 w = *reinterpret_cast<const float4*>(Wm + (size_t)o * DH_LD + tk * 4);
     const float2 a = *reinterpret_cast<const float2*>(Dt + (size_t)o * 36 + tm * 2);
     acc[0][0] = fmaf(a.x, w.x, acc[0][0]); acc[0][1] = fmaf(a.x, w.y, acc[0][1]);
     acc[0][2] = fmaf(a.x, w.z, acc[0][2]); acc[0][3] = fmaf(a.x, w.w, acc[0][3]);
@@ -434,8 +458,8 @@ k_head_dh(const __grid_constant__ HeadDesc d, const float* __restrict__ dz, cons
 // Layer-1 backward for B <= 32 rows: one pass over W1 produces BOTH the weight gradients
 //   g[o][k] = sum_m dh[m][o] * x[m][k]            (written straight into the flat gradient buffer)
 // and the input gradient  dx[m][k] = sum_s sum_o dh[m][s*H+o] * W1_s[o][k].
-// grid = (K1/32, 2 streams) launched as clusters of 2 CTAs along y: the advantage-stream CTA hands its
-// dx partial to the value-stream CTA through distributed shared memory (fixed order -> deterministic).
+// grid = (K1/32, 2 streams x 2 halves of the stream's rows) launched as clusters of 4 CTAs along y: three CTAs
+// hand their dx partial to rank 0 through distributed shared memory (fixed rank order -> deterministic).
 // 256 threads: warps 0-3 compute the weight-gradient tile of the current 32-row chunk of W1 while warps
 // 4-7 accumulate the input gradient from the same staged tiles; all 8 warps prefetch the next chunk.
 // ------------------------------------------------------------------------------------------------
@@ -443,7 +467,7 @@ constexpr int B1_K = 32;   // k columns per CTA
 constexpr int B1_O = 32;   // rows of W1 per chunk
 constexpr int B1_T = 256;  // threads
 
-__global__ void __cluster_dims__(1, 2, 1) __launch_bounds__(B1_T)
+__global__ void __cluster_dims__(1, 4, 1) __launch_bounds__(B1_T)
 k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrads g, const float* __restrict__ x,
             const float* __restrict__ dh, int B, float* __restrict__ dx) {
   __shared__ __align__(16) float Xs[32][B1_K + 4];    // x slice [m][k]
@@ -455,7 +479,9 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x;
   const int role = tid >> 7, rt = tid & 127, tk = rt & 15, to = rt >> 4;  // micro tile: 4 rows (o or m) x 2 k
-  const int s = blockIdx.y, k0 = blockIdx.x * B1_K, K = d.K1, H = d.H;
+  // cluster of 4 CTAs along y: (stream, half of the stream's W1 rows); rank 0 sums the four dx partials
+  const int s = blockIdx.y >> 1, half = blockIdx.y & 1, k0 = blockIdx.x * B1_K, K = d.K1, H = d.H;
+  const int o_begin = half * (H / 2), o_end = o_begin + H / 2;
   const float* __restrict__ mu = d.w1_mu[s];
   const float* __restrict__ sg = d.w1_sig[s];
   const float* ei = d.ei1[s];
@@ -498,11 +524,11 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
     if (st_c == 0) Eo[st_r] = peo;
   };
 
-  prefetch(0);
+  prefetch(o_begin);
   commit();
   __syncthreads();
-  for (int ob = 0; ob < H; ob += B1_O) {
-    const bool more = ob + B1_O < H;
+  for (int ob = o_begin; ob < o_end; ob += B1_O) {
+    const bool more = ob + B1_O < o_end;
     if (more) prefetch(ob + B1_O);
     if (role == 0) {
       // ---- weight gradient tile [32 o][32 k]: reduction over the batch rows ----
@@ -550,24 +576,31 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
       __syncthreads();
     }
   }
-  // ---- dx = value-stream partial + advantage-stream partial, over distributed shared memory ----
-  if (s == 1 && role == 1) {
+  // ---- dx = sum of the four partials (fixed rank order), over distributed shared memory ----
+  const unsigned rank = cluster.block_rank();
+  if (rank != 0 && role == 1) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) *reinterpret_cast<float2*>(&Red[to * 4 + i][tk * 2]) = make_float2(acc[i][0], acc[i][1]);
   }
   cluster.sync();
-  if (s == 0 && role == 1) {
-    const float* remote = cluster.map_shared_rank(&Red[0][0], 1);
+  if (rank == 0 && role == 1) {
+#pragma unroll
+    for (int r = 1; r < 4; ++r) {
+      const float* remote = cluster.map_shared_rank(&Red[0][0], r);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 v = *reinterpret_cast<const float2*>(remote + (to * 4 + i) * (B1_K + 4) + tk * 2);
+        acc[i][0] += v.x;
+        acc[i][1] += v.y;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int m = to * 4 + i;
-      if (m < B) {
-        const float2 r = *reinterpret_cast<const float2*>(remote + m * (B1_K + 4) + tk * 2);
-        *reinterpret_cast<float2*>(dx + (size_t)m * K + k0 + tk * 2) = make_float2(acc[i][0] + r.x, acc[i][1] + r.y);
-      }
+      if (m < B) *reinterpret_cast<float2*>(dx + (size_t)m * K + k0 + tk * 2) = make_float2(acc[i][0], acc[i][1]);
     }
   }
-  cluster.sync();  // the remote CTA's shared memory must outlive the reads above
+  cluster.sync();  // remote shared memory must outlive the reads above
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -621,9 +654,9 @@ int head_check(const rb_head_params* p, const char* who) {
 }
 
 void head_splits(int K1, int H, int* s1, int* s2, int* ks1, int* ks2) {
-  // aim for about one wave of 148 SMs for layer 1 (N tiles = 2H/64), slices are multiples of the 32-wide k tile
+  // aim for about two resident CTAs per SM (148 SMs) for layer 1 (N tiles = 2H/64), slices are multiples of the 32-wide k tile
   const int ntiles1 = 2 * H / NT;
-  int want = (148 + ntiles1 - 1) / ntiles1;
+  int want = (296 + ntiles1 - 1) / ntiles1;
   const int kt1 = (K1 + KT - 1) / KT;
   if (want > kt1) want = kt1;
   if (want > 16) want = 16;
@@ -669,16 +702,16 @@ int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const 
   {
     dim3 grid(tiles1, s1, mt);
     rbi::ProfScope prof_(RB_K_HEAD_FC1, st);
-    if (MT == 64) k_head_fc<64, 1><<<grid, HT, 0, st>>>(d, x_lo, m_lo, x_hi, M, part1, h, tickets, ks1);
-    else k_head_fc<32, 1><<<grid, HT, 0, st>>>(d, x_lo, m_lo, x_hi, M, part1, h, tickets, ks1);
+    if (MT == 64) k_head_fc<64, 1><<<grid, FC_T, 0, st>>>(d, x_lo, m_lo, x_hi, M, part1, h, tickets, ks1);
+    else k_head_fc<32, 1><<<grid, FC_T, 0, st>>>(d, x_lo, m_lo, x_hi, M, part1, h, tickets, ks1);
   }
   rc = rbi::check_launch("rb_head_forward(fc1)");
   if (rc != RB_OK) return rc;
   {
     dim3 grid(tiles2, s2, mt);
     rbi::ProfScope prof_(RB_K_HEAD_FC2, st);
-    if (MT == 64) k_head_fc<64, 2><<<grid, HT, 0, st>>>(d, h, M, nullptr, M, part2, z, tickets + 2048, ks2);
-    else k_head_fc<32, 2><<<grid, HT, 0, st>>>(d, h, M, nullptr, M, part2, z, tickets + 2048, ks2);
+    if (MT == 64) k_head_fc<64, 2><<<grid, FC_T, 0, st>>>(d, h, M, nullptr, M, part2, z, tickets + 2048, ks2);
+    else k_head_fc<32, 2><<<grid, FC_T, 0, st>>>(d, h, M, nullptr, M, part2, z, tickets + 2048, ks2);
   }
   return rbi::check_launch("rb_head_forward(fc2)");
 }
@@ -732,7 +765,7 @@ int rb_head_backward(const rb_head_params* p, const rb_head_grads* gr, const flo
   rc = rbi::check_launch("rb_head_backward(dh)");
   if (rc != RB_OK) return rc;
   {
-    dim3 grid(d.K1 / B1_K, 2);
+    dim3 grid(d.K1 / B1_K, 4);
     rbi::ProfScope prof_(RB_K_HEAD_BWD1, st);
     k_head_bwd1<<<grid, B1_T, 0, st>>>(d, g, x, dh_scratch, B, dx);
   }

@@ -138,7 +138,7 @@ k_tree_update(float* tree, int64_t tree_start, int64_t size, const int64_t* __re
 // with __match_any_sync, take the sibling value from the partner lane when the sibling is itself on an updated
 // path (else from the prefetched value), and the lowest lane of each group writes the node.  L dependent global
 // round trips (one per level, with a CTA barrier each) become one.
-constexpr int UPD_MAX_LEVELS = 40;
+constexpr int UPD_MAX_LEVELS = 30;
 
 __global__ void __launch_bounds__(32, 1)
 k_tree_update_warp(float* tree, int64_t tree_start, int64_t size, const int64_t* __restrict__ tree_idx,
@@ -167,7 +167,7 @@ k_tree_update_warp(float* tree, int64_t tree_start, int64_t size, const int64_t*
   vmax = warp_max(vmax);
   // duplicates: the highest lane (= last in index order) wins, memory.py:45 fancy assignment
   {
-    const long long key = active ? (long long)node : -(long long)(lane + 1);
+    const int key = active ? (int)node : -(lane + 1);   // node indices fit 31 bits (checked by the launcher)
     const unsigned grp = __match_any_sync(full, key);
     const int winner = 31 - __clz(grp);
     val = __shfl_sync(full, val, winner);
@@ -184,7 +184,7 @@ k_tree_update_warp(float* tree, int64_t tree_start, int64_t size, const int64_t*
     }
   }
   {
-    const long long key = active ? (long long)node : -(long long)(lane + 1);
+    const int key = active ? (int)node : -(lane + 1);
     const unsigned grp = __match_any_sync(full, key);
     if (active && lane == __ffs(grp) - 1) __stcg(tree + node, val);
   }
@@ -193,7 +193,7 @@ k_tree_update_warp(float* tree, int64_t tree_start, int64_t size, const int64_t*
     if (l < L) {
       const int64_t parent = active ? ((node - 1) >> 1) : -(int64_t)(lane + 1);
       const bool is_left = active && (node & 1);
-      const unsigned grp = __match_any_sync(full, (long long)parent);
+      const unsigned grp = __match_any_sync(full, (int)parent);
       const unsigned lefts = __ballot_sync(full, is_left);
       const unsigned other = grp & (is_left ? ~lefts : lefts);
       const float partner = __shfl_sync(full, val, other ? __ffs(other) - 1 : lane);
@@ -786,11 +786,25 @@ k_c51_dueling(const float* __restrict__ z_on, const float* __restrict__ z_tg, co
   float* zs = s_dyn;
   float* qs = s_dyn + (size_t)C51_WARPS * 3 * N2;
   const int i0 = blockIdx.x * C51_WARPS;
-  for (int idx = threadIdx.x; idx < C51_WARPS * 3 * N2; idx += blockDim.x) {
-    const int w = idx / (3 * N2), rem = idx - w * 3 * N2, t = rem / N2, c = rem - t * N2, i = i0 + w;
-    float v = 0.0f;
-    if (i < B) v = (t == 0) ? __ldg(z_on + (size_t)i * N2 + c) : (t == 1) ? __ldg(z_on + (size_t)(B + i) * N2 + c) : __ldg(z_tg + (size_t)i * N2 + c);
-    zs[idx] = v;
+  {
+    const int total = C51_WARPS * 3 * N2;
+    for (int base = threadIdx.x; base < total; base += blockDim.x * 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {  // eight independent loads in flight per thread, then the stores
+        const int idx = base + u * blockDim.x;
+        v[u] = 0.0f;
+        if (idx < total) {
+          const int w = idx / (3 * N2), rem = idx - w * 3 * N2, t = rem / N2, c = rem - t * N2, i = i0 + w;
+          if (i < B) v[u] = (t == 0) ? __ldg(z_on + (size_t)i * N2 + c) : (t == 1) ? __ldg(z_on + (size_t)(B + i) * N2 + c) : __ldg(z_tg + (size_t)i * N2 + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = base + u * blockDim.x;
+        if (idx < total) zs[idx] = v[u];
+      }
+    }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1100,7 +1114,7 @@ int rb_tree_update(float* tree, int64_t tree_start, int64_t size, const int64_t*
   if (!tree || !tree_idx || !raw_priority || !running_max) return fail(RB_ERR_INVAL, "rb_tree_update: null pointer");
   if (B <= 0 || size <= 0 || (size & 1)) return fail(RB_ERR_INVAL, "rb_tree_update: B > 0 and an even size are required");
   { ProfScope prof_(RB_K_TREE_UPDATE, (cudaStream_t)stream);
-    if (B <= 32 && tree_depth(tree_start) <= UPD_MAX_LEVELS)
+    if (B <= 32 && tree_depth(tree_start) <= 30)
       k_tree_update_warp<<<1, 32, 0, (cudaStream_t)stream>>>(tree, tree_start, size, tree_idx, raw_priority, omega,
                                                             omega_is_applied, B, running_max, status);
     else
