@@ -65,7 +65,7 @@ typedef void* rb_stream_t; /* cudaStream_t */
 enum {
   RB_K_TREE_UPDATE = 0, RB_K_TREE_FIND, RB_K_TREE_SAMPLE, RB_K_GATHER, RB_K_ITER_STATES, RB_K_APPEND, RB_K_C51,
   RB_K_NOISY_RESAMPLE, RB_K_NOISY_COMPOSE, RB_K_SQNORM, RB_K_CLIP_ADAM, RB_K_HEAD_FC1, RB_K_HEAD_FC2, RB_K_HEAD_LOGITS,
-  RB_K_HEAD_WGRAD2, RB_K_HEAD_DH, RB_K_HEAD_BWD1, RB_K_NOISE_FACTORS, RB_K_C51_DUELING, RB_KERNEL_COUNT
+  RB_K_HEAD_WGRAD2, RB_K_HEAD_DH, RB_K_HEAD_BWD1, RB_K_NOISE_FACTORS, RB_K_C51_DUELING, RB_K_BIAS_GRAD, RB_KERNEL_COUNT
 };
 
 int rb_abi_version(void);
@@ -199,9 +199,15 @@ int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const 
 int rb_head_logits(const float* z, int M, int actions, int atoms, float* q, rb_stream_t stream);
 
 /* Backward for B <= 32 rows: given dz[B][atoms*(1+actions)] (value block first), x[B][conv_features] and h[B][2*hidden]
- * writes all 16 parameter gradients through `g` and dx[B][conv_features].  dh_scratch: float32[B][2*hidden]. */
+ * writes all 16 parameter gradients through `g` and dx[B][conv_features].  dh_scratch: float32[B][2*hidden].
+ * relu_mask_x != 0 additionally zeroes dx where x <= 0, i.e. folds in the backward of the ReLU that produced the conv
+ * features (model.py:59), so dx is the gradient w.r.t. the last conv layer's pre-activation. */
 int rb_head_backward(const rb_head_params* p, const rb_head_grads* g, const float* x, const float* h, const float* dz, int B,
-                     float* dh_scratch, float* dx, rb_stream_t stream);
+                     float* dh_scratch, float* dx, int relu_mask_x, rb_stream_t stream);
+
+/* Bias gradient of a conv layer (the sum over batch and pixels torch computes in convolution_backward):
+ * out[c] = sum_{b,p} grad_out[b][c][p], grad_out float32[B][C][HW] contiguous. */
+int rb_bias_grad(const float* grad_out, int B, int C, int HW, float* out, rb_stream_t stream);
 
 /* rb_c51_loss_grad fed by the fused heads: z_online has 2B rows (s then s'), z_target B rows (s');
  * returns loss[B] and dz[B][atoms*(1+actions)] = d mean(w*loss) / d (z_value | z_advantage) of the online(s) rows

@@ -236,7 +236,13 @@ class Agent:
             x_ns = on.features_nograd(next_states)
             done_ns = torch.cuda.Event()
             done_ns.record(s_ns)
-        x_s = on.features(states)                      # autograd graph: convs only
+        manual = on.manual_conv_ok(states)
+        if manual:
+            with torch.no_grad():
+                acts = on.conv_forward_saving(states)  # library kernels, backward scheduled by hand below
+            x_s = acts[-1].view(B, -1)
+        else:
+            x_s = on.features(states)                  # autograd graph: convs only
         with torch.no_grad():
             xs_d = x_s.detach()
             main.wait_event(done_ns)
@@ -245,11 +251,18 @@ class Agent:
             main.wait_event(done_tg)
             loss, dz = c51_dueling_loss_grad(z_on, z_t, self.action_space, self.atoms, actions, returns, nonterminals, weights,
                                              self.support, self.Vmin, self.Vmax, self.delta_z, self.discount ** self.n)
-            self.optimiser.zero_conv_grad()
             dh = torch.empty((B, 2 * on.hidden_size), dtype=torch.float32, device=self.device)
             dx = torch.empty_like(xs_d)
-            on.head().backward(p_on, xs_d, h_on[:B], dz, dh, dx)           # writes the 16 head gradients + dx
-        x_s.backward(dx)
+            if manual:
+                # dx comes back already masked by the last conv layer's ReLU; conv gradients are overwritten
+                on.head().backward(p_on, xs_d, h_on[:B], dz, dh, dx, relu_mask_x=True)
+                grads_done = on.conv_backward_into_grads(acts, dx.view_as(acts[-1]), s_ns)
+                main.wait_event(grads_done)
+            else:
+                self.optimiser.zero_conv_grad()
+                on.head().backward(p_on, xs_d, h_on[:B], dz, dh, dx)       # writes the 16 head gradients + dx
+        if not manual:
+            x_s.backward(dx)
         self.sync.all_reduce_(self.optimiser.flat_grad)
         self.optimiser.step(grad_scale=1.0 / self.sync.world_size)
         return loss

@@ -469,7 +469,7 @@ constexpr int B1_T = 256;  // threads
 
 __global__ void __cluster_dims__(1, 4, 1) __launch_bounds__(B1_T)
 k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrads g, const float* __restrict__ x,
-            const float* __restrict__ dh, int B, float* __restrict__ dx) {
+            const float* __restrict__ dh, int B, float* __restrict__ dx, int relu_mask_x) {
   __shared__ __align__(16) float Xs[32][B1_K + 4];    // x slice [m][k]
   __shared__ __align__(16) float Ds[32][B1_O + 4];    // dh chunk [m][o]
   __shared__ __align__(16) float DsT[B1_O][32 + 4];   // dh chunk [o][m]
@@ -597,7 +597,15 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int m = to * 4 + i;
-      if (m < B) *reinterpret_cast<float2*>(dx + (size_t)m * K + k0 + tk * 2) = make_float2(acc[i][0], acc[i][1]);
+      if (m < B) {
+        float2 o2 = make_float2(acc[i][0], acc[i][1]);
+        if (relu_mask_x) {  // x = relu(conv output): fold that ReLU's backward in (x > 0 <=> pre-activation > 0)
+          const float2 xv = *reinterpret_cast<const float2*>(&Xs[m][tk * 2]);
+          o2.x = xv.x > 0.f ? o2.x : 0.f;
+          o2.y = xv.y > 0.f ? o2.y : 0.f;
+        }
+        *reinterpret_cast<float2*>(dx + (size_t)m * K + k0 + tk * 2) = o2;
+      }
     }
   }
   cluster.sync();  // remote shared memory must outlive the reads above
@@ -629,6 +637,28 @@ k_noise_factors(float* __restrict__ f_in, int n_in, float* __restrict__ f_out, i
   }
   __syncthreads();
   if (threadIdx.x == 0 && rng_counter && !x_in) *rng_counter = ctr + 1ull;
+}
+
+// Conv bias gradient: out[c] = sum over (batch, pixels) of g[b][c][hw].  One CTA per channel, fixed-order tree
+// reduction (deterministic); replaces a library reduction that runs this shape on 4 CTAs.
+__global__ void __launch_bounds__(256)
+k_bias_grad(const float* __restrict__ g, int B, int C, int HW, float* __restrict__ out) {
+  __shared__ float s_red[8];
+  const int c = blockIdx.x;
+  float acc = 0.0f;
+  for (int i = threadIdx.x; i < B * HW; i += 256) {
+    const int b = i / HW, p = i - b * HW;
+    acc += __ldg(g + ((size_t)b * C + c) * HW + p);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    out[c] = t;
+  }
 }
 
 int head_check(const rb_head_params* p, const char* who) {
@@ -726,7 +756,7 @@ int rb_head_logits(const float* z, int M, int actions, int atoms, float* q, rb_s
 }
 
 int rb_head_backward(const rb_head_params* p, const rb_head_grads* gr, const float* x, const float* h, const float* dz, int B,
-                     float* dh_scratch, float* dx, rb_stream_t stream) {
+                     float* dh_scratch, float* dx, int relu_mask_x, rb_stream_t stream) {
   int rc = head_check(p, "rb_head_backward: null pointer or bad size");
   if (rc != RB_OK) return rc;
   if (!gr || !x || !h || !dz || !dh_scratch || !dx) return rbi::fail(RB_ERR_INVAL, "rb_head_backward: null pointer");
@@ -767,9 +797,18 @@ int rb_head_backward(const rb_head_params* p, const rb_head_grads* gr, const flo
   {
     dim3 grid(d.K1 / B1_K, 4);
     rbi::ProfScope prof_(RB_K_HEAD_BWD1, st);
-    k_head_bwd1<<<grid, B1_T, 0, st>>>(d, g, x, dh_scratch, B, dx);
+    k_head_bwd1<<<grid, B1_T, 0, st>>>(d, g, x, dh_scratch, B, dx, relu_mask_x);
   }
   return rbi::check_launch("rb_head_backward(bwd1)");
+}
+
+int rb_bias_grad(const float* grad_out, int B, int C, int HW, float* out, rb_stream_t stream) {
+  if (!grad_out || !out || B <= 0 || C <= 0 || HW <= 0) return rbi::fail(RB_ERR_INVAL, "rb_bias_grad: bad argument");
+  {
+    rbi::ProfScope prof_(RB_K_BIAS_GRAD, (cudaStream_t)stream);
+    k_bias_grad<<<C, 256, 0, (cudaStream_t)stream>>>(grad_out, B, C, HW, out);
+  }
+  return rbi::check_launch("rb_bias_grad");
 }
 
 int rb_noise_factors(float* f_in, int n_in, float* f_out, int n_out, const float* x_in, const float* x_out, uint64_t seed,

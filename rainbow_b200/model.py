@@ -168,10 +168,10 @@ class FusedHead:
         _lib.check(self.lib.rb_head_logits(_lib.ptr(z), M, self.net.action_space, self.net.atoms, _lib.ptr(q), _lib.stream()))
         return q
 
-    def backward(self, p, x, h, dz, dh_scratch, dx):
+    def backward(self, p, x, h, dz, dh_scratch, dx, relu_mask_x=False):
         g = self.grads()
         _lib.check(self.lib.rb_head_backward(C.byref(p), C.byref(g), _lib.ptr(x), _lib.ptr(h), _lib.ptr(dz), x.shape[0],
-                                             _lib.ptr(dh_scratch), _lib.ptr(dx), _lib.stream()))
+                                             _lib.ptr(dh_scratch), _lib.ptr(dx), 1 if relu_mask_x else 0, _lib.stream()))
         return dx
 
 
@@ -269,6 +269,50 @@ class DQN(nn.Module):
 
     def features(self, x):
         return self.convs(x).view(-1, self.conv_output_size)
+
+    # ---- conv body with a hand-scheduled backward (library kernels, our schedule) -------------------------
+    def conv_layers(self):
+        return [m for m in self.convs if isinstance(m, nn.Conv2d)]
+
+    def manual_conv_ok(self, x):
+        return x.is_cuda and torch.backends.cudnn.enabled
+
+    def conv_forward_saving(self, x):
+        """Conv body through cuDNN's fused conv + bias + ReLU, keeping every layer's input for the manual backward.
+        Returns [a0 = x, a1, ..., aL] (aL = ReLU(conv_L(...)), the conv features)."""
+        acts = [x]
+        for m in self.conv_layers():
+            acts.append(torch.cudnn_convolution_relu(acts[-1], m.weight, m.bias, m.stride, m.padding, m.dilation, m.groups))
+        return acts
+
+    def conv_backward_into_grads(self, acts, g_last, side_stream):
+        """Backward of the conv body given g_last = d loss / d (pre-activation of the last conv layer).
+        The data-gradient chain (dgrad -> ReLU mask -> dgrad ...) runs on the current stream; the weight and bias
+        gradients, which nothing downstream waits for except the optimiser, run on `side_stream` and are written
+        straight into the parameters' .grad storage.  Returns the event the optimiser has to wait for."""
+        lib = _lib.load()
+        main = torch.cuda.current_stream(g_last.device)
+        layers = self.conv_layers()
+        g = g_last
+        for li in range(len(layers) - 1, -1, -1):
+            m, a_in = layers[li], acts[li]
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(side_stream):
+                side_stream.wait_event(ready)
+                g.record_stream(side_stream)
+                _, gw, _ = torch.ops.aten.convolution_backward(g, a_in, m.weight, None, m.stride, m.padding, m.dilation, False,
+                                                               [0, 0], m.groups, [False, True, False])
+                m.weight.grad.copy_(gw)
+                _lib.check(lib.rb_bias_grad(_lib.ptr(g), g.shape[0], g.shape[1], g.shape[2] * g.shape[3],
+                                            _lib.ptr(m.bias.grad), side_stream.cuda_stream))
+            if li > 0:
+                gin, _, _ = torch.ops.aten.convolution_backward(g, a_in, m.weight, None, m.stride, m.padding, m.dilation, False,
+                                                                [0, 0], m.groups, [True, False, False])
+                g = torch.ops.aten.threshold_backward(gin, a_in, 0.0)      # ReLU of the layer below (a_in = its output)
+        done = torch.cuda.Event()
+        done.record(side_stream)
+        return done
 
     def features_nograd(self, x):
         """Inference-only conv body: cuDNN's fused conv + bias + ReLU (one launch per layer instead of three).

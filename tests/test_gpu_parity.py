@@ -436,8 +436,9 @@ class FakeEnv:
         return self.a
 
 
-@pytest.mark.parametrize("fused", [True, False], ids=["fused_head", "library_gemm_head"])
-def test_learner_step_vs_reference_golden(fused):
+@pytest.mark.parametrize("fused,cudnn", [(True, True), (True, False), (False, True)],
+                         ids=["fused_head_manual_conv_bwd", "fused_head_autograd_convs", "library_gemm_head"])
+def test_learner_step_vs_reference_golden(fused, cudnn):
     """End to end: one Agent.learn on a tiny data-efficient net vs the unmodified reference CPU run
     (tests/golden/model_step.npz): same initial weights, same batch, same target-net noise draw.
     GPU conv/GEMM (fp32, TF32 off) vs CPU conv/GEMM: loss within 1e-5, gradients within 1e-6 abs."""
@@ -460,7 +461,9 @@ def test_learner_step_vs_reference_golden(fused):
     x_in = t(np.concatenate([g[f"target_randn{2 * i}"] for i in range(4)]))
     x_out = t(np.concatenate([g[f"target_randn{2 * i + 1}"] for i in range(4)]))
     assert ag._fused_path(B) == fused
-    loss = ag._update_from_batch(batch, target_noise=(x_in, x_out))
+    with torch.backends.cudnn.flags(enabled=cudnn):   # cuDNN off (main.py's default) -> convs go through autograd
+        assert ag.online_net.manual_conv_ok(states) == cudnn
+        loss = ag._update_from_batch(batch, target_noise=(x_in, x_out))
     np.testing.assert_allclose(cpu(loss), g["loss"], rtol=1e-5, atol=1e-5)
     for k, p in ag.online_net.named_parameters():
         # clip_grad_norm_ scales .grad in place in the reference when norm > 10; here the norm is < 10
