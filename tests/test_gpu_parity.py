@@ -461,7 +461,7 @@ def test_learner_step_vs_reference_golden(fused, cudnn):
     x_in = t(np.concatenate([g[f"target_randn{2 * i}"] for i in range(4)]))
     x_out = t(np.concatenate([g[f"target_randn{2 * i + 1}"] for i in range(4)]))
     assert ag._fused_path(B) == fused
-    with torch.backends.cudnn.flags(enabled=cudnn):   # cuDNN off (main.py's default) -> convs go through autograd
+    with torch.backends.cudnn.flags(enabled=cudnn, allow_tf32=False):   # cuDNN off (main.py's default) -> convs go through autograd
         assert ag.online_net.manual_conv_ok(states) == cudnn
         loss = ag._update_from_batch(batch, target_noise=(x_in, x_out))
     np.testing.assert_allclose(cpu(loss), g["loss"], rtol=1e-5, atol=1e-5)
