@@ -213,37 +213,80 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
     const float* __restrict__ bmu_t = (LAYER == 1) ? d.b1_mu[s] : d.b2_mu[s];
     const float* __restrict__ bsg_t = (LAYER == 1) ? d.b1_sig[s] : d.b2_sig[s];
     const size_t slice = (size_t)M * ncols;
+    // All loads of a batch are issued before any is consumed (fully unrolled, constant trip counts): the tail costs a
+    // couple of memory round trips instead of one per output element.
     if (LAYER == 1) {  // ncols = 2H and colbase + n0 are multiples of 4: float4 path
-      for (int idx = tid; idx < MT * (NT / 4); idx += FC_T) {
-        const int row = idx / (NT / 4), c = (idx % (NT / 4)) * 4, m = m0 + row, n = n0 + c;
-        if (m >= M || n >= Ns) continue;
-        const float* src = part + (size_t)m * ncols + colbase + n;
-        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 5
-        for (int sp = 0; sp < S; ++sp) {
-          const float4 pv = __ldcg(reinterpret_cast<const float4*>(src + sp * slice));
-          a4.x += pv.x; a4.y += pv.y; a4.z += pv.z; a4.w += pv.w;
-        }
+      constexpr int IT = MT * (NT / 4) / FC_T;  // float4 outputs per thread (2 or 4)
+      float4 a4[IT];
+      const float* src[IT];
+      bool ok[IT];
+#pragma unroll
+      for (int it = 0; it < IT; ++it) {
+        const int idx = tid + it * FC_T, row = idx / (NT / 4), c = (idx % (NT / 4)) * 4, m = m0 + row, n = n0 + c;
+        ok[it] = (m < M && n < Ns);
+        src[it] = part + (size_t)(ok[it] ? m : m0) * ncols + colbase + (ok[it] ? n : n0);
+        a4[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      for (int sp0 = 0; sp0 < S; sp0 += 4) {
+        float4 pv[IT][4];
+#pragma unroll
+        for (int it = 0; it < IT; ++it)
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            pv[it][u] = (sp0 + u < S) ? __ldcg(reinterpret_cast<const float4*>(src[it] + (size_t)(sp0 + u) * slice))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int it = 0; it < IT; ++it)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            a4[it].x += pv[it][u].x; a4[it].y += pv[it][u].y; a4[it].z += pv[it][u].z; a4[it].w += pv[it][u].w;
+          }
+      }
+#pragma unroll
+      for (int it = 0; it < IT; ++it) {
+        if (!ok[it]) continue;
+        const int idx = tid + it * FC_T, row = idx / (NT / 4), c = (idx % (NT / 4)) * 4, m = m0 + row, n = n0 + c;
         float4 bv = __ldg(reinterpret_cast<const float4*>(bmu_t + n));
         if (eo) {
           const float4 bs = __ldg(reinterpret_cast<const float4*>(bsg_t + n));
           const float4 e4 = __ldg(reinterpret_cast<const float4*>(eo + n));
           bv.x = fmaf(bs.x, e4.x, bv.x); bv.y = fmaf(bs.y, e4.y, bv.y); bv.z = fmaf(bs.z, e4.z, bv.z); bv.w = fmaf(bs.w, e4.w, bv.w);
         }
-        a4.x = fmaxf(a4.x + bv.x, 0.f); a4.y = fmaxf(a4.y + bv.y, 0.f); a4.z = fmaxf(a4.z + bv.z, 0.f); a4.w = fmaxf(a4.w + bv.w, 0.f);
-        *reinterpret_cast<float4*>(out + (size_t)m * ncols + colbase + n) = a4;
+        float4 r4;
+        r4.x = fmaxf(a4[it].x + bv.x, 0.f); r4.y = fmaxf(a4[it].y + bv.y, 0.f);
+        r4.z = fmaxf(a4[it].z + bv.z, 0.f); r4.w = fmaxf(a4[it].w + bv.w, 0.f);
+        *reinterpret_cast<float4*>(out + (size_t)m * ncols + colbase + n) = r4;
       }
     } else {
-      for (int idx = tid; idx < MT * NT; idx += FC_T) {
-        const int row = idx / NT, c = idx % NT, m = m0 + row, n = n0 + c;
-        if (m >= M || n >= Ns) continue;
-        const float* src = part + (size_t)m * ncols + colbase + n;
-        float a1 = 0.0f;
-#pragma unroll 4
-        for (int sp = 0; sp < S; ++sp) a1 += __ldcg(src + sp * slice);
-        float bv = __ldg(bmu_t + n);
-        if (eo) bv = fmaf(__ldg(bsg_t + n), __ldg(eo + n), bv);
-        out[(size_t)m * ncols + colbase + n] = a1 + bv;
+      constexpr int IT = MT * NT / FC_T;  // scalar outputs per thread (8 or 16), handled 8 at a time
+#pragma unroll 1
+      for (int h0 = 0; h0 < IT; h0 += 8) {
+        float a1[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) a1[it] = 0.0f;
+        for (int sp0 = 0; sp0 < S; sp0 += 4) {
+          float pv[8][4];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int idx = tid + (h0 + it) * FC_T, row = idx / NT, c = idx % NT, m = m0 + row, n = n0 + c;
+            const bool okk = (m < M && n < Ns);
+            const float* sp = part + (size_t)(okk ? m : m0) * ncols + colbase + (okk ? n : n0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) pv[it][u] = (okk && sp0 + u < S) ? __ldcg(sp + (size_t)(sp0 + u) * slice) : 0.0f;
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a1[it] += pv[it][u];
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int idx = tid + (h0 + it) * FC_T, row = idx / NT, c = idx % NT, m = m0 + row, n = n0 + c;
+          if (m >= M || n >= Ns) continue;
+          float bv = __ldg(bmu_t + n);
+          if (eo) bv = fmaf(__ldg(bsg_t + n), __ldg(eo + n), bv);
+          out[(size_t)m * ncols + colbase + n] = a1[it] + bv;
+        }
       }
     }
     return;

@@ -592,7 +592,7 @@ k_append(float* tree, int64_t tree_start, int64_t size, uint8_t* __restrict__ fr
 // warp-private shared memory for the dueling entry point) and returns, per lane, the gradient row
 // g[z] = (w/B)(p*sum(m) - m) of the taken action.
 constexpr int C51_WARPS = 4;
-constexpr int C51_R = RB_MAX_ATOMS / 32;
+// atoms per lane: templates are instantiated for R = 2 (Z <= 64, the usual 51 atoms) and R = 4 (Z <= 128)
 
 struct C51Scratch {  // per warp
   float pt[RB_MAX_ATOMS];  // target probabilities p(s', a*)
@@ -601,6 +601,7 @@ struct C51Scratch {  // per warp
   int u[RB_MAX_ATOMS];
 };
 
+template <int C51_R>
 __device__ __forceinline__ void softmax_row(const float* row, int Z, int lane, float (&e)[C51_R], float (&x)[C51_R],
                                             float& mx, float& sum) {
   mx = -CUDART_INF_F;
@@ -621,6 +622,7 @@ __device__ __forceinline__ void softmax_row(const float* row, int Z, int lane, f
 }
 
 // q_on_ns / q_tg_ns: A rows of Z (row stride Z); q_on_s_act: the row of the taken action.
+template <int C51_R>
 __device__ __forceinline__ void c51_core(C51Scratch& sc, int lane, int i, int B, int A, int Z, const float* q_on_ns,
                                          const float* q_tg_ns, const float* q_on_s_act, float ret, float nonterminal,
                                          float weight, const float* __restrict__ support, float vmin, float vmax,
@@ -744,6 +746,7 @@ __device__ __forceinline__ void c51_core(C51Scratch& sc, int lane, int i, int B,
   __syncwarp();
 }
 
+template <int C51_R>
 __global__ void __launch_bounds__(C51_WARPS * 32)
 k_c51(const float* __restrict__ q_on_s, const float* __restrict__ q_on_ns, const float* __restrict__ q_tg_ns,
       const int64_t* __restrict__ actions, const float* __restrict__ returns, const float* __restrict__ nonterminals,
@@ -756,7 +759,7 @@ k_c51(const float* __restrict__ q_on_s, const float* __restrict__ q_on_ns, const
   if (i >= B) return;
   const int act = (int)actions[i];
   float g[C51_R];
-  c51_core(s_sc[warp], lane, i, B, A, Z, q_on_ns + (size_t)i * A * Z, q_tg_ns + (size_t)i * A * Z,
+  c51_core<C51_R>(s_sc[warp], lane, i, B, A, Z, q_on_ns + (size_t)i * A * Z, q_tg_ns + (size_t)i * A * Z,
            q_on_s + ((size_t)i * A + act) * Z, __ldg(returns + i), __ldg(nonterminals + i), __ldg(weights + i), support, vmin,
            vmax, delta_z, gamma_n, loss, m_out, astar_out, g);
   float* gq = grad + (size_t)i * A * Z;
@@ -774,6 +777,7 @@ k_c51(const float* __restrict__ q_on_s, const float* __restrict__ q_on_ns, const
 // shared memory with coalesced loads, each warp assembles its logit rows
 // q[a][z] = zv[z] + za[a][z] - mean_a za[.][z] (model.py:73-75) there, and the gradient is returned w.r.t.
 // the head outputs:  dzv[z] = g[z],  dza[a][z] = g[z] * ([a == act] - 1/A).
+template <int C51_R>
 __global__ void __launch_bounds__(C51_WARPS * 32)
 k_c51_dueling(const float* __restrict__ z_on, const float* __restrict__ z_tg, const int64_t* __restrict__ actions,
               const float* __restrict__ returns, const float* __restrict__ nonterminals, const float* __restrict__ weights,
@@ -840,7 +844,7 @@ k_c51_dueling(const float* __restrict__ z_on, const float* __restrict__ z_tg, co
   }
   __syncwarp();
   float g[C51_R];
-  c51_core(s_sc[warp], lane, i, B, A, Z, q_ns, q_t, q_s, __ldg(returns + i), __ldg(nonterminals + i), __ldg(weights + i),
+  c51_core<C51_R>(s_sc[warp], lane, i, B, A, Z, q_ns, q_t, q_s, __ldg(returns + i), __ldg(nonterminals + i), __ldg(weights + i),
            support, vmin, vmax, delta_z, gamma_n, loss, m_out, astar_out, g);
   float* dzi = dz + (size_t)i * N2;
 #pragma unroll
@@ -1214,9 +1218,14 @@ int rb_c51_loss_grad(const float* q_online_s, const float* q_online_ns, const fl
   if (Z > RB_MAX_ATOMS) return fail(RB_ERR_RANGE, "rb_c51_loss_grad: Z exceeds RB_MAX_ATOMS");
   const int ctas = (B + C51_WARPS - 1) / C51_WARPS;
   { ProfScope prof_(RB_K_C51, (cudaStream_t)stream);
-    k_c51<<<ctas, C51_WARPS * 32, 0, (cudaStream_t)stream>>>(q_online_s, q_online_ns, q_target_ns, actions, returns,
-                                                          nonterminals, weights, support, vmin, vmax, delta_z, gamma_n, B,
-                                                          A, Z, loss, grad_q_online_s, m_out, astar_out); }
+    if (Z <= 64)
+      k_c51<2><<<ctas, C51_WARPS * 32, 0, (cudaStream_t)stream>>>(q_online_s, q_online_ns, q_target_ns, actions, returns,
+                                                               nonterminals, weights, support, vmin, vmax, delta_z, gamma_n,
+                                                               B, A, Z, loss, grad_q_online_s, m_out, astar_out);
+    else
+      k_c51<4><<<ctas, C51_WARPS * 32, 0, (cudaStream_t)stream>>>(q_online_s, q_online_ns, q_target_ns, actions, returns,
+                                                               nonterminals, weights, support, vmin, vmax, delta_z, gamma_n,
+                                                               B, A, Z, loss, grad_q_online_s, m_out, astar_out); }
   return check_launch("rb_c51_loss_grad");
 }
 
@@ -1293,14 +1302,20 @@ int rb_c51_dueling_loss_grad(const float* z_online, const float* z_target, int a
   const size_t smem = (size_t)C51_WARPS * (3 * (Z + A * Z) + 2 * A * Z + Z) * sizeof(float);
   if (smem > 200 * 1024) return fail(RB_ERR_RANGE, "rb_c51_dueling_loss_grad: actions * atoms too large");
   if (smem > 40 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_c51_dueling, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_c51_dueling<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_c51_dueling<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(RB_ERR_CUDA, cudaGetErrorString(e));
   }
   const int ctas = (B + C51_WARPS - 1) / C51_WARPS;
   { ProfScope prof_(RB_K_C51_DUELING, (cudaStream_t)stream);
-    k_c51_dueling<<<ctas, C51_WARPS * 32, smem, (cudaStream_t)stream>>>(z_online, z_target, actions, returns, nonterminals, weights,
-                                                                      support, vmin, vmax, delta_z, gamma_n, B, A, Z, loss, dz,
-                                                                      m_out, astar_out); }
+    if (Z <= 64)
+      k_c51_dueling<2><<<ctas, C51_WARPS * 32, smem, (cudaStream_t)stream>>>(z_online, z_target, actions, returns, nonterminals,
+                                                                           weights, support, vmin, vmax, delta_z, gamma_n, B, A,
+                                                                           Z, loss, dz, m_out, astar_out);
+    else
+      k_c51_dueling<4><<<ctas, C51_WARPS * 32, smem, (cudaStream_t)stream>>>(z_online, z_target, actions, returns, nonterminals,
+                                                                           weights, support, vmin, vmax, delta_z, gamma_n, B, A,
+                                                                           Z, loss, dz, m_out, astar_out); }
   return check_launch("rb_c51_dueling_loss_grad");
 }
 
