@@ -201,9 +201,16 @@ int rb_head_logits(const float* z, int M, int actions, int atoms, float* q, rb_s
 /* Backward for B <= 32 rows: given dz[B][atoms*(1+actions)] (value block first), x[B][conv_features] and h[B][2*hidden]
  * writes all 16 parameter gradients through `g` and dx[B][conv_features].  dh_scratch: float32[B][2*hidden].
  * relu_mask_x != 0 additionally zeroes dx where x <= 0, i.e. folds in the backward of the ReLU that produced the conv
- * features (model.py:59), so dx is the gradient w.r.t. the last conv layer's pre-activation. */
+ * features (model.py:59), so dx is the gradient w.r.t. the last conv layer's pre-activation.
+ * `parts` selects which of the three launches to enqueue (so a caller can put the independent layer-2 weight
+ * gradient on another stream): RB_HEAD_BWD_WGRAD2 (layer-2 parameter gradients), RB_HEAD_BWD_DH (dh_scratch),
+ * RB_HEAD_BWD_LAYER1 (layer-1 parameter gradients + dx; needs dh_scratch); RB_HEAD_BWD_ALL = all, in that order. */
+#define RB_HEAD_BWD_WGRAD2 1
+#define RB_HEAD_BWD_DH 2
+#define RB_HEAD_BWD_LAYER1 4
+#define RB_HEAD_BWD_ALL 7
 int rb_head_backward(const rb_head_params* p, const rb_head_grads* g, const float* x, const float* h, const float* dz, int B,
-                     float* dh_scratch, float* dx, int relu_mask_x, rb_stream_t stream);
+                     float* dh_scratch, float* dx, int relu_mask_x, int parts, rb_stream_t stream);
 
 /* Bias gradient of a conv layer (the sum over batch and pixels torch computes in convolution_backward):
  * out[c] = sum_{b,p} grad_out[b][c][p], grad_out float32[B][C][HW] contiguous. */

@@ -48,7 +48,7 @@ SIGNATURES = {
     "rb_head_ticket_count": (C.c_int, []),
     "rb_head_forward": (C.c_int, [_hp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rb_head_logits": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
-    "rb_head_backward": (C.c_int, [_hp, _hg, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
+    "rb_head_backward": (C.c_int, [_hp, _hg, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp]),
     "rb_bias_grad": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "rb_c51_dueling_loss_grad": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32,
                                            _vp, _vp, _vp, _vp, _vp]),

@@ -254,16 +254,40 @@ class Agent:
             dh = torch.empty((B, 2 * on.hidden_size), dtype=torch.float32, device=self.device)
             dx = torch.empty_like(xs_d)
             if manual:
-                # dx comes back already masked by the last conv layer's ReLU; conv gradients are overwritten
-                on.head().backward(p_on, xs_d, h_on[:B], dz, dh, dx, relu_mask_x=True)
+                # dx comes back already masked by the last conv layer's ReLU; conv gradients are overwritten.
+                # The layer-2 weight gradient feeds nothing but the optimiser: it runs beside the dh -> layer-1 chain.
+                hd = on.head()
+                dz_ready = torch.cuda.Event()
+                dz_ready.record(main)
+                with torch.cuda.stream(s_tg):
+                    s_tg.wait_event(dz_ready)
+                    hd.backward(p_on, xs_d, h_on[:B], dz, dh, dx, parts=hd.BWD_WGRAD2)
+                    w2_done = torch.cuda.Event()
+                    w2_done.record(s_tg)
+                hd.backward(p_on, xs_d, h_on[:B], dz, dh, dx, relu_mask_x=True, parts=hd.BWD_DH | hd.BWD_LAYER1)
+                main.wait_event(w2_done)
+                head_ready = None
+                if self.sync.enabled:
+                    # 99 % of the gradient bytes (the noisy head) are final here: start their all-reduce on a side
+                    # stream so it overlaps the conv backward; the conv slice (a few hundred KB) follows afterwards
+                    head_ready = torch.cuda.Event()
+                    head_ready.record(main)
+                    with torch.cuda.stream(s_tg):
+                        s_tg.wait_event(head_ready)
+                        self.sync.all_reduce_(self.optimiser.flat_grad[self.optimiser.conv_end:])
+                        head_reduced = torch.cuda.Event()
+                        head_reduced.record(s_tg)
                 grads_done = on.conv_backward_into_grads(acts, dx.view_as(acts[-1]), s_ns)
                 main.wait_event(grads_done)
+                if self.sync.enabled:
+                    self.sync.all_reduce_(self.optimiser.flat_grad[:self.optimiser.conv_end])
+                    main.wait_event(head_reduced)
             else:
                 self.optimiser.zero_conv_grad()
                 on.head().backward(p_on, xs_d, h_on[:B], dz, dh, dx)       # writes the 16 head gradients + dx
         if not manual:
             x_s.backward(dx)
-        self.sync.all_reduce_(self.optimiser.flat_grad)
+            self.sync.all_reduce_(self.optimiser.flat_grad)
         self.optimiser.step(grad_scale=1.0 / self.sync.world_size)
         return loss
 

@@ -799,8 +799,9 @@ int rb_head_logits(const float* z, int M, int actions, int atoms, float* q, rb_s
 }
 
 int rb_head_backward(const rb_head_params* p, const rb_head_grads* gr, const float* x, const float* h, const float* dz, int B,
-                     float* dh_scratch, float* dx, int relu_mask_x, rb_stream_t stream) {
+                     float* dh_scratch, float* dx, int relu_mask_x, int parts, rb_stream_t stream) {
   int rc = head_check(p, "rb_head_backward: null pointer or bad size");
+  if ((parts & 7) == 0) return rbi::fail(RB_ERR_INVAL, "rb_head_backward: parts must select at least one of RB_HEAD_BWD_*");
   if (rc != RB_OK) return rc;
   if (!gr || !x || !h || !dz || !dh_scratch || !dx) return rbi::fail(RB_ERR_INVAL, "rb_head_backward: null pointer");
   if (B <= 0 || B > 32) return rbi::fail(RB_ERR_RANGE, "rb_head_backward: 1 <= B <= 32 required (larger batches use the library GEMM path)");
@@ -814,7 +815,7 @@ int rb_head_backward(const rb_head_params* p, const rb_head_grads* gr, const flo
   }
   const HeadDesc d = to_desc(p);
   cudaStream_t st = (cudaStream_t)stream;
-  {
+  if (parts & RB_HEAD_BWD_WGRAD2) {
     const int tiles = (d.Z + NT - 1) / NT + (d.A * d.Z + NT - 1) / NT;
     dim3 grid(tiles, d.H / NT);
     rbi::ProfScope prof_(RB_K_HEAD_WGRAD2, st);
@@ -822,7 +823,7 @@ int rb_head_backward(const rb_head_params* p, const rb_head_grads* gr, const flo
   }
   rc = rbi::check_launch("rb_head_backward(wgrad2)");
   if (rc != RB_OK) return rc;
-  {
+  if (parts & RB_HEAD_BWD_DH) {
     const int ns_max = d.A * d.Z > d.Z ? d.A * d.Z : d.Z;
     int ns_pad = (ns_max + 3) & ~3;
     if (ns_pad > 384) ns_pad = 384;
@@ -837,7 +838,7 @@ int rb_head_backward(const rb_head_params* p, const rb_head_grads* gr, const flo
   }
   rc = rbi::check_launch("rb_head_backward(dh)");
   if (rc != RB_OK) return rc;
-  {
+  if (parts & RB_HEAD_BWD_LAYER1) {
     dim3 grid(d.K1 / B1_K, 4);
     rbi::ProfScope prof_(RB_K_HEAD_BWD1, st);
     k_head_bwd1<<<grid, B1_T, 0, st>>>(d, g, x, dh_scratch, B, dx, relu_mask_x);

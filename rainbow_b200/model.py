@@ -168,10 +168,13 @@ class FusedHead:
         _lib.check(self.lib.rb_head_logits(_lib.ptr(z), M, self.net.action_space, self.net.atoms, _lib.ptr(q), _lib.stream()))
         return q
 
-    def backward(self, p, x, h, dz, dh_scratch, dx, relu_mask_x=False):
+    BWD_WGRAD2, BWD_DH, BWD_LAYER1, BWD_ALL = 1, 2, 4, 7
+
+    def backward(self, p, x, h, dz, dh_scratch, dx, relu_mask_x=False, parts=7):
         g = self.grads()
         _lib.check(self.lib.rb_head_backward(C.byref(p), C.byref(g), _lib.ptr(x), _lib.ptr(h), _lib.ptr(dz), x.shape[0],
-                                             _lib.ptr(dh_scratch), _lib.ptr(dx), 1 if relu_mask_x else 0, _lib.stream()))
+                                             _lib.ptr(dh_scratch), _lib.ptr(dx), 1 if relu_mask_x else 0, parts,
+                                             _lib.stream()))
         return dx
 
 
