@@ -326,21 +326,40 @@ def ours(opts, cfg, rank, world, local):
     log(f"value region: {ms_value / K:.3f} ms/step")
     # ---- e2e: public API with host frames ------------------------------------------------------------
     host_frames = [torch.rand(4, 84, 84).pin_memory() for _ in range(8)]
-    loss_host = torch.empty(B, dtype=torch.float32).pin_memory()
+    loss_host = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_seen = {"sum": 0.0, "n": 0, "pending": [False, False]}
+
+    def consume(slot):
+        if loss_seen["pending"][slot]:
+            loss_evt[slot].synchronize()                 # the host really reads every step's loss ...
+            loss_seen["sum"] += float(loss_host[slot].sum())
+            loss_seen["n"] += 1
+            loss_seen["pending"][slot] = False
 
     def e2e_step(i):
         for j in range(REPLAY_FREQUENCY):
             mem.append(host_frames[(i + j) % 8], (i + j) % ACTIONS, float((i % 3) - 1), (i * 4 + j) % 1000 == 999)
         step()
-        loss_host.copy_(agent.last_loss, non_blocking=False)  # D2H read of the step's result (syncs, like agent.py:100)
+        slot = i & 1
+        consume(slot)                                    # ... one step behind the GPU (double-buffered pinned copy),
+        loss_host[slot].copy_(agent.last_loss, non_blocking=True)   # so the launch thread is not stalled every step
+        loss_evt[slot].record()
+        loss_seen["pending"][slot] = True
 
     for i in range(W):
         e2e_step(i)
-    ms_e2e = timed(e2e_step, K)
-    log(f"e2e region: {ms_e2e / K:.3f} ms/step")
+    def e2e_region(i):
+        e2e_step(i)
+        if i == K - 1:                                   # drain inside the timed region: every loss has reached the host
+            consume(0)
+            consume(1)
+
+    ms_e2e = timed(e2e_region, K)
+    log(f"e2e region: {ms_e2e / K:.3f} ms/step ({loss_seen['n']} losses read back)")
     clocks = sampler.finish()
     mem.check_last_sample()
-    assert np.isfinite(loss_host.numpy()).all()
+    assert np.isfinite(loss_seen["sum"]) and loss_seen["n"] >= K
 
     # ---- per-kernel durations: eager pass, CUDA events around every hand-written kernel -------------------
     agent.use_cuda_graph = False
@@ -397,7 +416,7 @@ def ours(opts, cfg, rank, world, local):
             "e2e": {"value": e2e_value, "unit": "updates/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": REPLAY_FREQUENCY * 84 * 84 * 4, "d2h_bytes_per_step": B * 4,
                     "what": f"per step: {REPLAY_FREQUENCY} x mem.append(frame from pinned host memory) + dqn.reset_noise() + dqn.learn(mem) + "
-                            "per-sample loss copied to the host"},
+                            "per-sample loss copied to pinned host memory and read by the host one step behind the GPU (double buffer)"},
             # our kernels launched in the timed `value` region, per step: 2 k_noise_factors, k_tree_sample, k_gather,
             # 2 x (k_head_fc<.,1> + k_head_fc<.,2>), k_c51_dueling, k_head_wgrad2, k_head_dh, k_head_bwd1, k_sqnorm, k_clip_adam,
             # k_bump_step, k_tree_update = 16
