@@ -401,10 +401,10 @@ k_head_wgrad2(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGr
 }
 
 // Layer-2 backward, input gradient with the ReLU mask of layer 1 folded in:
-// dh[m][s*H + k] = (h > 0) * sum_o dz[m][col(o)] * W2_s[o][k].   grid = (H/32, 2), B <= 32 rows.
-// The CTA's whole [Ns x 32] slab of mu and sigma is fetched with ONE batch of cp.async (all loads in flight
-// at once: a single memory latency instead of one per chunk), dz is staged transposed, W2 is composed
-// on the fly from the raw tiles.
+// dh[m][s*H + k] = (h > 0) * sum_o dz[m][col(o)] * W2_s[o][k].   B <= 32 rows.
+// grid = (H/32, 2 streams x 4 row ranges), launched as 4-CTA clusters: each CTA fetches its [rows x 32] slab of mu and
+// sigma with ONE batch of cp.async (all loads in flight at once: a single memory latency), stages its dz slice
+// transposed, composes W2 in place, and the four partial tiles are summed over distributed shared memory.
 constexpr int DH_K = 32;
 constexpr int DH_LD = DH_K + 4;
 
@@ -414,16 +414,22 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
 
-__global__ void __launch_bounds__(HT)
+constexpr int DH_SPLIT = 4;  // CTAs per cluster: the stream's rows of W2 are split four ways
+
+__global__ void __cluster_dims__(1, DH_SPLIT, 1) __launch_bounds__(HT)
 k_head_dh(const __grid_constant__ HeadDesc d, const float* __restrict__ dz, const float* __restrict__ h, int B,
-          float* __restrict__ dh, int ns_pad) {
+          float* __restrict__ dh, int rows_pad) {
   extern __shared__ __align__(16) float smem_dh[];
-  float* Wm = smem_dh;                          // [ns_pad][DH_LD] raw mu
-  float* Wsg = Wm + (size_t)ns_pad * DH_LD;     // [ns_pad][DH_LD] raw sigma
-  float* Dt = Wsg + (size_t)ns_pad * DH_LD;     // [ns_pad][36]    dz transposed [o][m]
+  float* Wm = smem_dh;                           // [rows_pad][DH_LD] raw mu, composed in place
+  float* Wsg = Wm + (size_t)rows_pad * DH_LD;    // [rows_pad][DH_LD] raw sigma
+  float* Dt = Wsg + (size_t)rows_pad * DH_LD;    // [rows_pad][36]    dz transposed [o][m]
+  __shared__ __align__(16) float Red[32][DH_LD]; // partial tile handed over the cluster
+  cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, tk = tid & 7, tm = tid >> 3;  // micro tile: 2 rows (m) x 4 k
-  const int s = blockIdx.y, k0 = blockIdx.x * DH_K;
+  const int s = blockIdx.y / DH_SPLIT, q = blockIdx.y % DH_SPLIT, k0 = blockIdx.x * DH_K;
   const int Ns = n2_of(d, s), colbase = col2_of(d, s), ncols = d.Z + d.A * d.Z;
+  const int per = (Ns + DH_SPLIT - 1) / DH_SPLIT;
+  const int ob = q * per, nb = max(0, min(per, Ns - ob));   // this CTA's rows [ob, ob + nb)
   const float* ei = d.ei2[s];
   const float* eo = d.eo2[s];
   float acc[2][4];
@@ -431,15 +437,13 @@ k_head_dh(const __grid_constant__ HeadDesc d, const float* __restrict__ dz, cons
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-  for (int ob = 0; ob < Ns; ob += ns_pad) {  // one pass unless actions*atoms exceeds the slab (ns_pad rows)
-  const int nb = min(ns_pad, Ns - ob);
-  if (ob) __syncthreads();
+  // the whole slab in one batch of cp.async: a single memory latency
   for (int idx = tid; idx < nb * (DH_K / 4); idx += HT) {
     const int o = idx >> 3, k4 = (idx & 7) * 4;
     cp_async16(Wm + (size_t)o * DH_LD + k4, d.w2_mu[s] + (size_t)(ob + o) * d.H + k0 + k4);
     if (ei) cp_async16(Wsg + (size_t)o * DH_LD + k4, d.w2_sig[s] + (size_t)(ob + o) * d.H + k0 + k4);
   }
-  for (int base = tid; base < 32 * nb; base += HT * 8) {  // dz chunk, transposed; 8 loads in flight per thread
+  for (int base = tid; base < 32 * nb; base += HT * 8) {  // dz slice, transposed; 8 loads in flight per thread
     float v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -483,18 +487,37 @@ k_head_dh(const __grid_constant__ HeadDesc d, const float* __restrict__ dz, cons
     acc[1][0] = fmaf(a.y, w.x, acc[1][0]); acc[1][1] = fmaf(a.y, w.y, acc[1][1]);
     acc[1][2] = fmaf(a.y, w.z, acc[1][2]); acc[1][3] = fmaf(a.y, w.w, acc[1][3]);
   }
-  }
+  // ---- sum the four row-range partials in fixed rank order over distributed shared memory ----
+  const unsigned rank = cluster.block_rank();
+  if (rank != 0) {
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int m = tm * 2 + i;
-    if (m >= B) continue;
-    const size_t off = (size_t)m * (2 * d.H) + s * d.H + k0 + tk * 4;
-    const float4 hv = __ldg(reinterpret_cast<const float4*>(h + off));
-    float4 o4;
-    o4.x = hv.x > 0.f ? acc[i][0] : 0.f; o4.y = hv.y > 0.f ? acc[i][1] : 0.f;
-    o4.z = hv.z > 0.f ? acc[i][2] : 0.f; o4.w = hv.w > 0.f ? acc[i][3] : 0.f;
-    *reinterpret_cast<float4*>(dh + off) = o4;
+    for (int i = 0; i < 2; ++i)
+      *reinterpret_cast<float4*>(&Red[tm * 2 + i][tk * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   }
+  cluster.sync();
+  if (rank == 0) {
+#pragma unroll
+    for (int r = 1; r < DH_SPLIT; ++r) {
+      const float* remote = cluster.map_shared_rank(&Red[0][0], r);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float4 v = *reinterpret_cast<const float4*>(remote + (tm * 2 + i) * DH_LD + tk * 4);
+        acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int m = tm * 2 + i;
+      if (m >= B) continue;
+      const size_t off = (size_t)m * (2 * d.H) + s * d.H + k0 + tk * 4;
+      const float4 hv = __ldg(reinterpret_cast<const float4*>(h + off));
+      float4 o4;
+      o4.x = hv.x > 0.f ? acc[i][0] : 0.f; o4.y = hv.y > 0.f ? acc[i][1] : 0.f;
+      o4.z = hv.z > 0.f ? acc[i][2] : 0.f; o4.w = hv.w > 0.f ? acc[i][3] : 0.f;
+      *reinterpret_cast<float4*>(dh + off) = o4;
+    }
+  }
+  cluster.sync();  // remote shared memory must outlive the reads above
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -825,16 +848,16 @@ int rb_head_backward(const rb_head_params* p, const rb_head_grads* gr, const flo
   if (rc != RB_OK) return rc;
   if (parts & RB_HEAD_BWD_DH) {
     const int ns_max = d.A * d.Z > d.Z ? d.A * d.Z : d.Z;
-    int ns_pad = (ns_max + 3) & ~3;
-    if (ns_pad > 384) ns_pad = 384;
-    const size_t smem = (size_t)ns_pad * (2 * DH_LD + 36) * sizeof(float);
-    if (smem > 48 * 1024) {
+    const int rows_pad = (((ns_max + DH_SPLIT - 1) / DH_SPLIT) + 3) & ~3;
+    const size_t smem = (size_t)rows_pad * (2 * DH_LD + 36) * sizeof(float);
+    if (smem > 200 * 1024) return rbi::fail(RB_ERR_RANGE, "rb_head_backward: actions * atoms too large for the dh kernel");
+    if (smem > 40 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(k_head_dh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return rbi::fail(RB_ERR_CUDA, cudaGetErrorString(e));
     }
-    dim3 grid(d.H / DH_K, 2);
+    dim3 grid(d.H / DH_K, 2 * DH_SPLIT);
     rbi::ProfScope prof_(RB_K_HEAD_DH, st);
-    k_head_dh<<<grid, HT, smem, st>>>(d, dz, h, B, dh_scratch, ns_pad);
+    k_head_dh<<<grid, HT, smem, st>>>(d, dz, h, B, dh_scratch, rows_pad);
   }
   rc = rbi::check_launch("rb_head_backward(dh)");
   if (rc != RB_OK) return rc;

@@ -640,11 +640,30 @@ __device__ __forceinline__ void c51_core(C51Scratch& sc, int lane, int i, int B,
   int best = 0;
   float best_ev = -CUDART_INF_F;
   for (int a = 0; a < A; ++a) {
-    softmax_row(q_on_ns + (size_t)a * Z, Z, lane, e, x, mx, sum);
-    float ev = 0.0f;
+    // expected value sum_z support_z * p_z with p = e / sum(e): the numerator and sum(e) ride the same shuffle
+    // butterfly (two independent shuffles per step) and one division finishes the row
+    const float* row = q_on_ns + (size_t)a * Z;
+    mx = -CUDART_INF_F;
 #pragma unroll
-    for (int r = 0; r < C51_R; ++r) ev = __fadd_rn(ev, __fmul_rn(sup[r], __fdiv_rn(e[r], sum)));
-    ev = warp_sum(ev);
+    for (int r = 0; r < C51_R; ++r) {
+      int z = lane + 32 * r;
+      x[r] = (z < Z) ? row[z] : -CUDART_INF_F;
+      mx = fmaxf(mx, x[r]);
+    }
+    mx = warp_max(mx);
+    float se = 0.0f, sn = 0.0f;
+#pragma unroll
+    for (int r = 0; r < C51_R; ++r) {
+      const float ee = (lane + 32 * r < Z) ? expf(x[r] - mx) : 0.0f;
+      se = __fadd_rn(se, ee);
+      sn = __fadd_rn(sn, __fmul_rn(sup[r], ee));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      se = __fadd_rn(se, __shfl_xor_sync(0xffffffffu, se, o));
+      sn = __fadd_rn(sn, __shfl_xor_sync(0xffffffffu, sn, o));
+    }
+    const float ev = __fdiv_rn(sn, se);
     if (ev > best_ev) {  // first maximum wins, like torch.argmax
       best_ev = ev;
       best = a;
