@@ -61,6 +61,17 @@ HeadDesc to_desc(const rb_head_params* p) {
 __device__ __forceinline__ int n2_of(const HeadDesc& d, int s) { return s == 0 ? d.Z : d.A * d.Z; }
 __device__ __forceinline__ int col2_of(const HeadDesc& d, int s) { return s == 0 ? 0 : d.Z; }
 
+constexpr int FC_STAGES = 3;
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // Forward: C[m][n] (partial over a K slice) = sum_k A[m][k] * W[n][k],  W composed while staging.
 // grid = (n tiles over both streams, k slices, m tiles), block = 128, micro tile (MT/8) x 4.
@@ -101,65 +112,71 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
-  constexpr int A_PER = MT * (KT / 4) / FC_T;  // float4 per thread for the A tile (1 or 2)
+  // ---- 3-stage cp.async pipeline: raw tiles (A, mu, sigma; k contiguous) land in shared memory two tiles ahead of
+  // the one being multiplied; a transform pass composes W and transposes both operands into the compute buffers ----
+  constexpr int A_PER = MT * (KT / 4) / FC_T;  // 16-byte chunks per thread for the A tile (1 or 2)
   constexpr int B_PER = NT * (KT / 4) / FC_T;  // 2
-  float4 ra[A_PER], rmu[B_PER], rsg[B_PER];
+  constexpr int LDR = KT + 4;                  // raw row stride (floats): 144 B, keeps 16-byte alignment
+  constexpr int STAGE = (MT + 2 * NT) * LDR;   // floats per stage
+  extern __shared__ __align__(16) float fc_raw[];
+  auto Araw = [&](int st) { return fc_raw + (size_t)st * STAGE; };
+  auto Mraw = [&](int st) { return fc_raw + (size_t)st * STAGE + MT * LDR; };
+  auto Sraw = [&](int st) { return fc_raw + (size_t)st * STAGE + (MT + NT) * LDR; };
 
-  auto load_tile = [&](int k0) {
+  auto issue_tile = [&](int k0, int st) {
+    if (k0 < k_end) {
 #pragma unroll
-    for (int j = 0; j < A_PER; ++j) {
-      const int idx = tid + j * FC_T, row = idx >> 3, k = k0 + (idx & 7) * 4, m = m0 + row;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < M && k < k_end) {
-        if (LAYER == 1) {
-          const float* src = (m < m_lo) ? x_lo + (size_t)m * K : x_hi + (size_t)(m - m_lo) * K;
-          v = __ldg(reinterpret_cast<const float4*>(src + k));
-        } else {  // x_lo = h [M][2H] written by the layer-1 launch
-          v = __ldg(reinterpret_cast<const float4*>(x_lo + (size_t)m * (2 * d.H) + s * d.H + k));
+      for (int j = 0; j < A_PER; ++j) {
+        const int idx = tid + j * FC_T, row = idx >> 3, kk = (idx & 7) * 4, k = k0 + kk, m = m0 + row;
+        const bool ok = (m < M && k < k_end);
+        const float* src = x_lo;
+        if (ok) {
+          if (LAYER == 1) src = ((m < m_lo) ? x_lo + (size_t)m * K : x_hi + (size_t)(m - m_lo) * K) + k;
+          else src = x_lo + (size_t)m * (2 * d.H) + s * d.H + k;   // x_lo = h [M][2H] from the layer-1 launch
         }
+        cp_async16_zfill(Araw(st) + row * LDR + kk, src, ok);
       }
-      ra[j] = v;
-    }
 #pragma unroll
-    for (int j = 0; j < B_PER; ++j) {
-      const int idx = tid + j * FC_T, row = idx >> 3, k = k0 + (idx & 7) * 4, n = n0 + row;
-      float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = m4;
-      if (n < Ns && k < k_end) {
-        m4 = __ldg(reinterpret_cast<const float4*>(mu + (size_t)n * K + k));
-        if (ei) s4 = __ldg(reinterpret_cast<const float4*>(sg + (size_t)n * K + k));
+      for (int j = 0; j < B_PER; ++j) {
+        const int idx = tid + j * FC_T, row = idx >> 3, kk = (idx & 7) * 4, k = k0 + kk, n = n0 + row;
+        const bool ok = (n < Ns && k < k_end);
+        cp_async16_zfill(Mraw(st) + row * LDR + kk, ok ? mu + (size_t)n * K + k : mu, ok);
+        if (ei) cp_async16_zfill(Sraw(st) + row * LDR + kk, ok ? sg + (size_t)n * K + k : sg, ok);
       }
-      rmu[j] = m4;
-      rsg[j] = s4;
     }
+    cp_async_commit();   // always commit (possibly empty) so the group accounting stays uniform
   };
-  auto store_tile = [&](int k0) {
+  auto transform_tile = [&](int k0, int st) {
 #pragma unroll
     for (int j = 0; j < A_PER; ++j) {
       const int idx = tid + j * FC_T, row = idx >> 3, kk = (idx & 7) * 4;
-      As[kk + 0][row] = ra[j].x; As[kk + 1][row] = ra[j].y; As[kk + 2][row] = ra[j].z; As[kk + 3][row] = ra[j].w;
+      const float4 v = *reinterpret_cast<const float4*>(Araw(st) + row * LDR + kk);
+      As[kk + 0][row] = v.x; As[kk + 1][row] = v.y; As[kk + 2][row] = v.z; As[kk + 3][row] = v.w;
     }
 #pragma unroll
     for (int j = 0; j < B_PER; ++j) {
       const int idx = tid + j * FC_T, row = idx >> 3, kk = (idx & 7) * 4, k = k0 + kk, n = n0 + row;
-      float4 w = rmu[j];
+      float4 w = *reinterpret_cast<const float4*>(Mraw(st) + row * LDR + kk);
       if (ei && n < Ns && k < k_end) {  // compose W = mu + sigma * (eps_out[n] * eps_in[k])   (model.py:39,43)
+        const float4 sg4 = *reinterpret_cast<const float4*>(Sraw(st) + row * LDR + kk);
         const float e = __ldg(eo + n);
         const float4 e4 = __ldg(reinterpret_cast<const float4*>(ei + k));
-        w.x = fmaf(rsg[j].x, e * e4.x, w.x); w.y = fmaf(rsg[j].y, e * e4.y, w.y);
-        w.z = fmaf(rsg[j].z, e * e4.z, w.z); w.w = fmaf(rsg[j].w, e * e4.w, w.w);
+        w.x = fmaf(sg4.x, e * e4.x, w.x); w.y = fmaf(sg4.y, e * e4.y, w.y);
+        w.z = fmaf(sg4.z, e * e4.z, w.z); w.w = fmaf(sg4.w, e * e4.w, w.w);
       }
       Bs[kk + 0][row] = w.x; Bs[kk + 1][row] = w.y; Bs[kk + 2][row] = w.z; Bs[kk + 3][row] = w.w;
     }
   };
 
-  if (k_begin < k_end) {
-    load_tile(k_begin);
-    store_tile(k_begin);
-  }
-  __syncthreads();
+  issue_tile(k_begin, 0);
+  issue_tile(k_begin + KT, 1);
+  int stage = 0;
   for (int k0 = k_begin; k0 < k_end; k0 += KT) {
-    const bool more = k0 + KT < k_end;
-    if (more) load_tile(k0 + KT);  // global loads in flight while this tile is consumed
+    issue_tile(k0 + 2 * KT, (stage + 2) % FC_STAGES);
+    cp_async_wait<FC_STAGES - 1>();   // this thread's copies of tile k0 have landed ...
+    __syncthreads();                  // ... and everybody else's
+    transform_tile(k0, stage);
+    __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < KT; ++kk) {
       float a[TM];
@@ -177,12 +194,10 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
         acc[i][2] = fmaf(a[i], b.z, acc[i][2]); acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
       }
     }
-    __syncthreads();
-    if (more) {
-      store_tile(k0 + KT);
-      __syncthreads();
-    }
+    __syncthreads();                  // As/Bs and raw stage `stage` are free again
+    stage = (stage + 1) % FC_STAGES;
   }
+  cp_async_wait<0>();
   const int S = gridDim.y;
   if (S > 1) {
 #pragma unroll
@@ -795,19 +810,30 @@ int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const 
   const int mt = (M + MT - 1) / MT;
   const int tiles1 = 2 * d.H / NT, tiles2 = (d.Z + NT - 1) / NT + (d.A * d.Z + NT - 1) / NT;
   if (mt > 65535 || mt * tiles1 > 2048 || mt * tiles2 > 2048) return rbi::fail(RB_ERR_RANGE, "rb_head_forward: too many rows");
+  const size_t smem64 = (size_t)FC_STAGES * (64 + 2 * NT) * (KT + 4) * sizeof(float);
+  const size_t smem32 = (size_t)FC_STAGES * (32 + 2 * NT) * (KT + 4) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k_head_fc<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_head_fc<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_head_fc<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_head_fc<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+    if (e != cudaSuccess) return rbi::fail(RB_ERR_CUDA, cudaGetErrorString(e));
+    attr_done = true;
+  }
   {
     dim3 grid(tiles1, s1, mt);
     rbi::ProfScope prof_(RB_K_HEAD_FC1, st);
-    if (MT == 64) k_head_fc<64, 1><<<grid, FC_T, 0, st>>>(d, x_lo, m_lo, x_hi, M, part1, h, tickets, ks1);
-    else k_head_fc<32, 1><<<grid, FC_T, 0, st>>>(d, x_lo, m_lo, x_hi, M, part1, h, tickets, ks1);
+    if (MT == 64) k_head_fc<64, 1><<<grid, FC_T, smem64, st>>>(d, x_lo, m_lo, x_hi, M, part1, h, tickets, ks1);
+    else k_head_fc<32, 1><<<grid, FC_T, smem32, st>>>(d, x_lo, m_lo, x_hi, M, part1, h, tickets, ks1);
   }
   rc = rbi::check_launch("rb_head_forward(fc1)");
   if (rc != RB_OK) return rc;
   {
     dim3 grid(tiles2, s2, mt);
     rbi::ProfScope prof_(RB_K_HEAD_FC2, st);
-    if (MT == 64) k_head_fc<64, 2><<<grid, FC_T, 0, st>>>(d, h, M, nullptr, M, part2, z, tickets + 2048, ks2);
-    else k_head_fc<32, 2><<<grid, FC_T, 0, st>>>(d, h, M, nullptr, M, part2, z, tickets + 2048, ks2);
+    if (MT == 64) k_head_fc<64, 2><<<grid, FC_T, smem64, st>>>(d, h, M, nullptr, M, part2, z, tickets + 2048, ks2);
+    else k_head_fc<32, 2><<<grid, FC_T, smem32, st>>>(d, h, M, nullptr, M, part2, z, tickets + 2048, ks2);
   }
   return rbi::check_launch("rb_head_forward(fc2)");
 }
