@@ -85,10 +85,10 @@ template <int MT, int LAYER>
 __global__ void __launch_bounds__(FC_T, 2)
 k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, int m_lo, const float* __restrict__ x_hi,
           int M, float* __restrict__ part, float* __restrict__ out, int* __restrict__ tickets, int kslice) {
-  constexpr int TM = MT / 16;  // 256 threads = 16 (m groups) x 16 (n groups of 4): micro tile TM x 4
-  constexpr int LDA = MT + 4;
-  __shared__ __align__(16) float As[KT][LDA];
-  __shared__ __align__(16) float Bs[KT][LDB];
+  // 256 threads = 16 (ty) x 16 (tx).  Thread (ty, tx) owns rows m0 + ty + 16*i (i < TM) and columns n0 + tx + 16*j
+  // (j < 4): with the raw tiles kept [row][k] (k contiguous, row stride 36 floats) both operands are read as
+  // conflict-free float4 along k, so no transposed copy of the tiles is ever made.
+  constexpr int TM = MT / 16;
 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int K = (LAYER == 1) ? d.K1 : d.H;
@@ -113,7 +113,7 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
   // ---- 3-stage cp.async pipeline: raw tiles (A, mu, sigma; k contiguous) land in shared memory two tiles ahead of
-  // the one being multiplied; a transform pass composes W and transposes both operands into the compute buffers ----
+  // the one being multiplied; the noisy weights are composed in place and both operands are consumed straight from the raw tiles ----
   constexpr int A_PER = MT * (KT / 4) / FC_T;  // 16-byte chunks per thread for the A tile (1 or 2)
   constexpr int B_PER = NT * (KT / 4) / FC_T;  // 2
   constexpr int LDR = KT + 4;                  // raw row stride (floats): 144 B, keeps 16-byte alignment
@@ -146,25 +146,19 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
     }
     cp_async_commit();   // always commit (possibly empty) so the group accounting stays uniform
   };
-  auto transform_tile = [&](int k0, int st) {
-#pragma unroll
-    for (int j = 0; j < A_PER; ++j) {
-      const int idx = tid + j * FC_T, row = idx >> 3, kk = (idx & 7) * 4;
-      const float4 v = *reinterpret_cast<const float4*>(Araw(st) + row * LDR + kk);
-      As[kk + 0][row] = v.x; As[kk + 1][row] = v.y; As[kk + 2][row] = v.z; As[kk + 3][row] = v.w;
-    }
+  auto compose_tile = [&](int k0, int st) {   // W = mu + sigma * (eps_out[n] * eps_in[k]) in place   (model.py:39,43)
 #pragma unroll
     for (int j = 0; j < B_PER; ++j) {
       const int idx = tid + j * FC_T, row = idx >> 3, kk = (idx & 7) * 4, k = k0 + kk, n = n0 + row;
-      float4 w = *reinterpret_cast<const float4*>(Mraw(st) + row * LDR + kk);
-      if (ei && n < Ns && k < k_end) {  // compose W = mu + sigma * (eps_out[n] * eps_in[k])   (model.py:39,43)
+      if (n < Ns && k < k_end) {
+        float4 w = *reinterpret_cast<const float4*>(Mraw(st) + row * LDR + kk);
         const float4 sg4 = *reinterpret_cast<const float4*>(Sraw(st) + row * LDR + kk);
         const float e = __ldg(eo + n);
         const float4 e4 = __ldg(reinterpret_cast<const float4*>(ei + k));
         w.x = fmaf(sg4.x, e * e4.x, w.x); w.y = fmaf(sg4.y, e * e4.y, w.y);
         w.z = fmaf(sg4.z, e * e4.z, w.z); w.w = fmaf(sg4.w, e * e4.w, w.w);
+        *reinterpret_cast<float4*>(Mraw(st) + row * LDR + kk) = w;
       }
-      Bs[kk + 0][row] = w.x; Bs[kk + 1][row] = w.y; Bs[kk + 2][row] = w.z; Bs[kk + 3][row] = w.w;
     }
   };
 
@@ -172,29 +166,32 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
   issue_tile(k_begin + KT, 1);
   int stage = 0;
   for (int k0 = k_begin; k0 < k_end; k0 += KT) {
-    issue_tile(k0 + 2 * KT, (stage + 2) % FC_STAGES);
-    cp_async_wait<FC_STAGES - 1>();   // this thread's copies of tile k0 have landed ...
-    __syncthreads();                  // ... and everybody else's
-    transform_tile(k0, stage);
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < KT; ++kk) {
-      float a[TM];
-      if (TM == 4) {
-        const float4 t = *reinterpret_cast<const float4*>(&As[kk][ty * TM]);
-        a[0] = t.x; a[1] = t.y; a[TM - 2] = t.z; a[TM - 1] = t.w;
-      } else {
-        const float2 t = *reinterpret_cast<const float2*>(&As[kk][ty * TM]);
-        a[0] = t.x; a[1] = t.y;
-      }
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-#pragma unroll
-      for (int i = 0; i < TM; ++i) {
-        acc[i][0] = fmaf(a[i], b.x, acc[i][0]); acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
-        acc[i][2] = fmaf(a[i], b.z, acc[i][2]); acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
-      }
+    cp_async_wait<FC_STAGES - 2>();   // this thread's copies of tile k0 have landed ...
+    __syncthreads();                  // ... and everybody else's; everybody is also done with the previous tile
+    issue_tile(k0 + 2 * KT, (stage + 2) % FC_STAGES);   // overwrites the stage the previous tile used
+    if (ei) {
+      compose_tile(k0, stage);
+      __syncthreads();
     }
-    __syncthreads();                  // As/Bs and raw stage `stage` are free again
+    const float* At = Araw(stage) + ty * LDR;
+    const float* Bt = Mraw(stage) + tx * LDR;
+#pragma unroll
+    for (int k4 = 0; k4 < KT; k4 += 4) {
+      float4 a[TM], b[4];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(At + i * 16 * LDR + k4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(Bt + j * 16 * LDR + k4);
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+          acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+          acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+          acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+        }
+    }
     stage = (stage + 1) % FC_STAGES;
   }
   cp_async_wait<0>();
@@ -202,12 +199,12 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
   if (S > 1) {
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
-      const int m = m0 + ty * TM + i;
+      const int m = m0 + ty + 16 * i;
       if (m >= M) continue;
       float* dst = part + ((size_t)blockIdx.y * M + m) * ncols + colbase;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int n = n0 + tx * 4 + j;
+        const int n = n0 + tx + 16 * j;
         if (n < Ns) __stcg(dst + n, acc[i][j]);
       }
     }
@@ -312,7 +309,7 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
   float bias[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int n = n0 + tx * 4 + j;
+    const int n = n0 + tx + 16 * j;
     bias[j] = 0.0f;
     if (n < Ns) {
       bias[j] = __ldg(bmu + n);
@@ -321,12 +318,12 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
   }
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
-    const int m = m0 + ty * TM + i;
+    const int m = m0 + ty + 16 * i;
     if (m >= M) continue;
     float* dst = out + (size_t)m * ncols + colbase;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+      const int n = n0 + tx + 16 * j;
       if (n < Ns) {
         const float v = acc[i][j] + bias[j];
         dst[n] = (LAYER == 1) ? fmaxf(v, 0.0f) : v;
