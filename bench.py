@@ -199,7 +199,7 @@ def reference_arm(opts, cfg, rank):
                                        f"after {min(5, max(3, opts.warmup))} warm-up updates; replay tree/gather in C (oracle), nets in torch-CPU "
                                        f"with {threads} threads"},
             "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(name, cfg, gpus):
@@ -393,7 +393,8 @@ def ours(opts, cfg, rank, world, local):
             kernels[name] = {"us": round(us, 2), "bytes": alg[name], "GBps": round(gbs, 1), "frac": round(gbs / peak, 4),
                              "launches_timed": cnt}
     step_kernel_us = {k: kernels[k]["us"] * launches_per_step.get(k, 0) for k in kernels}
-    dominant = max(step_kernel_us, key=step_kernel_us.get)
+    # dominant hand-written kernel = the longest single launch of the step (it also moves the most bytes)
+    dominant = max((k for k in kernels if launches_per_step.get(k, 0)), key=lambda k: kernels[k]["us"])
     d = kernels[dominant]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu --set full capture
@@ -427,10 +428,37 @@ def ours(opts, cfg, rank, world, local):
         line["cpu_baseline"] = {"value": ups, "unit": "updates/s", "cores": threads, "kind": "port",
                                 "sample": f"{n_cpu} updates of the same workload (each preceded by {REPLAY_FREQUENCY} appends) after 3 warm-up "
                                           f"updates, {dt:.1f} s; oracle port: replay in C, nets in torch-CPU"}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+class StdoutGuard:
+    """Keeps fd 1 clean: libraries (NCCL prints its version banner there) write to stderr instead, and only the
+    final JSON line goes to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+
+GUARD = None
+
+
+def emit(obj):
+    line = json.dumps(obj)
+    if GUARD is not None:
+        GUARD.emit(line)
+    else:
+        print(line, flush=True)
 
 
 def main():
+    global GUARD
+    GUARD = StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)

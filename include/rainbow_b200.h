@@ -187,6 +187,8 @@ typedef struct rb_head_grads {   /* gradients are OVERWRITTEN (not accumulated) 
  * tickets is int32[rb_head_ticket_count()], zero-initialised ONCE by the caller (the kernels leave it zeroed). */
 int rb_head_splits(int conv_features, int hidden, int* s1, int* s2);
 int rb_head_ticket_count(void);
+/* timing probes only: bit 0 skips the layer-1 launch of rb_head_forward, bit 1 the layer-2 launch (0 = normal) */
+int rb_head_debug(int flags);
 
 /* Forward over M = m_lo + m_hi rows (x_lo: [m_lo][conv_features], x_hi: [m_hi][conv_features] or NULL).
  * Outputs: h[M][2*hidden] (post-ReLU hidden activations, value stream in columns [0,hidden), advantage stream in

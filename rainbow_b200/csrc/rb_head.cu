@@ -792,6 +792,12 @@ int rb_head_splits(int conv_features, int hidden, int* s1, int* s2) {
 
 int rb_head_ticket_count(void) { return 4096; }
 
+static int g_head_debug = 0;   // bit 0: skip the layer-1 launch, bit 1: skip the layer-2 launch (timing probes only)
+int rb_head_debug(int flags) {
+  g_head_debug = flags;
+  return RB_OK;
+}
+
 int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const float* x_hi, int m_hi, float* part1, float* part2,
                     int32_t* tickets, float* h, float* z, rb_stream_t stream) {
   int rc = head_check(p, "rb_head_forward: null pointer or bad size");
@@ -818,7 +824,7 @@ int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const 
     if (e != cudaSuccess) return rbi::fail(RB_ERR_CUDA, cudaGetErrorString(e));
     attr_done = true;
   }
-  {
+  if (!(g_head_debug & 1)) {
     dim3 grid(tiles1, s1, mt);
     rbi::ProfScope prof_(RB_K_HEAD_FC1, st);
     if (MT == 64) k_head_fc<64, 1><<<grid, FC_T, smem64, st>>>(d, x_lo, m_lo, x_hi, M, part1, h, tickets, ks1);
@@ -826,7 +832,7 @@ int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const 
   }
   rc = rbi::check_launch("rb_head_forward(fc1)");
   if (rc != RB_OK) return rc;
-  {
+  if (!(g_head_debug & 2)) {
     dim3 grid(tiles2, s2, mt);
     rbi::ProfScope prof_(RB_K_HEAD_FC2, st);
     if (MT == 64) k_head_fc<64, 2><<<grid, FC_T, smem64, st>>>(d, h, M, nullptr, M, part2, z, tickets + 2048, ks2);

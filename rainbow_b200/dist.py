@@ -18,6 +18,10 @@ def init_from_env(backend=None):
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
+        # NVLS (in-switch reduction) is left off unless the caller asks for it: a 4-of-8-GPU launch on this pool
+        # hung in communicator setup with it on, while the 27 MB gradient all-reduce is overlapped with the conv
+        # backward anyway (export NCCL_NVLS_ENABLE=1 to turn it back on)
+        os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":

@@ -67,6 +67,15 @@ with torch.no_grad():
     x_ns = on.features(nstates)
     timeit("head fwd online (2B rows)", lambda: on.head().forward(x_s, x_ns))
     timeit("head fwd target (B rows)", lambda: tg.head().forward(x_ns))
+    from rainbow_b200 import _lib
+    L = _lib.load()
+    L.rb_head_debug(2)
+    timeit("  fc1 only, online (2B rows)", lambda: on.head().forward(x_s, x_ns))
+    timeit("  fc1 only, target (B rows)", lambda: tg.head().forward(x_ns))
+    L.rb_head_debug(1)
+    timeit("  fc2 only, online (2B rows)", lambda: on.head().forward(x_s, x_ns))
+    timeit("  fc2 only, target (B rows)", lambda: tg.head().forward(x_ns))
+    L.rb_head_debug(0)
     z_on, h_on, p_on = on.head().forward(x_s, x_ns)
     z_t, _, _ = tg.head().forward(x_ns)
     z_t = z_t.clone()
@@ -77,6 +86,9 @@ with torch.no_grad():
     dh = torch.empty(B, 2 * on.hidden_size, device=dev)
     dx = torch.empty_like(x_s)
     timeit("head backward (3 kernels)", lambda: on.head().backward(p_on, x_s, h_on[:B], dz, dh, dx))
+    timeit("  wgrad2 only", lambda: on.head().backward(p_on, x_s, h_on[:B], dz, dh, dx, parts=1))
+    timeit("  dh only", lambda: on.head().backward(p_on, x_s, h_on[:B], dz, dh, dx, parts=2))
+    timeit("  bwd1 only", lambda: on.head().backward(p_on, x_s, h_on[:B], dz, dh, dx, parts=4))
     timeit("zero conv grads", lambda: ag.optimiser.zero_conv_grad())
 
 
