@@ -815,15 +815,11 @@ int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const 
   if (mt > 65535 || mt * tiles1 > 2048 || mt * tiles2 > 2048) return rbi::fail(RB_ERR_RANGE, "rb_head_forward: too many rows");
   const size_t smem64 = (size_t)FC_STAGES * (64 + 2 * NT) * (KT + 4) * sizeof(float);
   const size_t smem32 = (size_t)FC_STAGES * (32 + 2 * NT) * (KT + 4) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_head_fc<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_head_fc<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_head_fc<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_head_fc<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
-    if (e != cudaSuccess) return rbi::fail(RB_ERR_CUDA, cudaGetErrorString(e));
-    attr_done = true;
-  }
+  rc = rbi::ensure_dynamic_smem(k_head_fc<64, 1>, smem64, "rb_head_forward");
+  if (rc == RB_OK) rc = rbi::ensure_dynamic_smem(k_head_fc<64, 2>, smem64, "rb_head_forward");
+  if (rc == RB_OK) rc = rbi::ensure_dynamic_smem(k_head_fc<32, 1>, smem32, "rb_head_forward");
+  if (rc == RB_OK) rc = rbi::ensure_dynamic_smem(k_head_fc<32, 2>, smem32, "rb_head_forward");
+  if (rc != RB_OK) return rc;
   if (!(g_head_debug & 1)) {
     dim3 grid(tiles1, s1, mt);
     rbi::ProfScope prof_(RB_K_HEAD_FC1, st);
@@ -880,10 +876,8 @@ int rb_head_backward(const rb_head_params* p, const rb_head_grads* gr, const flo
     const int rows_pad = (((ns_max + DH_SPLIT - 1) / DH_SPLIT) + 3) & ~3;
     const size_t smem = (size_t)rows_pad * (2 * DH_LD + 36) * sizeof(float);
     if (smem > 200 * 1024) return rbi::fail(RB_ERR_RANGE, "rb_head_backward: actions * atoms too large for the dh kernel");
-    if (smem > 40 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(k_head_dh, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return rbi::fail(RB_ERR_CUDA, cudaGetErrorString(e));
-    }
+    rc = rbi::ensure_dynamic_smem(k_head_dh, smem, "rb_head_backward");
+    if (rc != RB_OK) return rc;
     dim3 grid(d.H / DH_K, 2 * DH_SPLIT);
     rbi::ProfScope prof_(RB_K_HEAD_DH, st);
     k_head_dh<<<grid, HT, smem, st>>>(d, dz, h, B, dh_scratch, rows_pad);

@@ -25,6 +25,48 @@ inline int check_launch(const char* what) {
   return RB_OK;
 }
 
+// ---- opt-in to more than 48 KB of dynamic shared memory, once per (device, kernel, size) ---------------
+// cudaFuncSetAttribute is not a stream operation; calling it again and again (e.g. while a CUDA graph is being
+// captured) is avoided by remembering the largest size already granted per device.
+struct SmemGrant {
+  const void* fn;
+  int dev;
+  size_t bytes;
+};
+SmemGrant* smem_grants();   // table of 256 entries, zero-initialised (defined in rb_kernels.cu)
+
+template <typename Kernel>
+inline int ensure_dynamic_smem(Kernel kernel, size_t bytes, const char* who) {
+  if (bytes <= 48 * 1024) return RB_OK;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(RB_ERR_CUDA, who);
+  const void* fn = reinterpret_cast<const void*>(kernel);
+  SmemGrant* t = smem_grants();
+  int slot = -1;
+  for (int i = 0; i < 256; ++i) {
+    if (t[i].fn == fn && t[i].dev == dev) {
+      if (t[i].bytes >= bytes) return RB_OK;
+      slot = i;
+      break;
+    }
+    if (t[i].fn == nullptr) {
+      slot = i;
+      break;
+    }
+  }
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    snprintf(err_buffer(), 256, "%s: %s", who, cudaGetErrorString(e));
+    return RB_ERR_CUDA;
+  }
+  if (slot >= 0) {
+    t[slot].fn = fn;
+    t[slot].dev = dev;
+    t[slot].bytes = bytes;
+  }
+  return RB_OK;
+}
+
 // ---- optional per-kernel timing: CUDA events recorded on the launching stream around a launch ----
 constexpr int PROF_SLOTS = 2048;
 struct ProfKernel {

@@ -27,6 +27,8 @@ thread_local char g_err[256] = "";
 char* err_buffer() { return g_err; }
 bool g_prof_on = false;
 ProfKernel g_prof[RB_KERNEL_COUNT];
+SmemGrant g_smem_grants[256] = {};
+SmemGrant* smem_grants() { return g_smem_grants; }
 bool& prof_on() { return g_prof_on; }
 ProfKernel* prof_table() { return g_prof; }
 }  // namespace rbi
@@ -1281,9 +1283,9 @@ static int noisy_launch(float* const* weight_eps, float* const* bias_eps, const 
   }
   plan.cta_begin[n_layers] = ctas;
   const size_t smem = (size_t)max_in * sizeof(float);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_noisy_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(RB_ERR_CUDA, cudaGetErrorString(e));
+  {
+    int rc_s = rbi::ensure_dynamic_smem(k_noisy_resample, smem, "rb_noisy_resample");
+    if (rc_s != RB_OK) return rc_s;
   }
   { ProfScope prof_(RB_K_NOISY_RESAMPLE, (cudaStream_t)stream);
     k_noisy_resample<<<ctas, NOISY_THREADS, smem, (cudaStream_t)stream>>>(plan, x_in, x_out, seed,
@@ -1320,11 +1322,9 @@ int rb_c51_dueling_loss_grad(const float* z_online, const float* z_target, int a
   if (Z > RB_MAX_ATOMS) return fail(RB_ERR_RANGE, "rb_c51_dueling_loss_grad: atoms exceeds RB_MAX_ATOMS");
   const size_t smem = (size_t)C51_WARPS * (3 * (Z + A * Z) + 2 * A * Z + Z) * sizeof(float);
   if (smem > 200 * 1024) return fail(RB_ERR_RANGE, "rb_c51_dueling_loss_grad: actions * atoms too large");
-  if (smem > 40 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_c51_dueling<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_c51_dueling<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(RB_ERR_CUDA, cudaGetErrorString(e));
-  }
+  int rc_s = rbi::ensure_dynamic_smem(k_c51_dueling<2>, smem, "rb_c51_dueling_loss_grad");
+  if (rc_s == RB_OK) rc_s = rbi::ensure_dynamic_smem(k_c51_dueling<4>, smem, "rb_c51_dueling_loss_grad");
+  if (rc_s != RB_OK) return rc_s;
   const int ctas = (B + C51_WARPS - 1) / C51_WARPS;
   { ProfScope prof_(RB_K_C51_DUELING, (cudaStream_t)stream);
     if (Z <= 64)
