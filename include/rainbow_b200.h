@@ -235,7 +235,8 @@ int rb_noisy_compose(const float* mu, const float* sigma, const float* eps, int6
  * elements (all online-net parameters laid out back to back).  `step_count` is a device int64 holding
  * the number of steps already taken; the kernel increments it.  grad_scale multiplies the gradient
  * before everything else (1/world_size after a SUM all-reduce; 1.0 on one GPU).
- * partial_sums: scratch float64[rb_clip_adam_scratch_elems()].  norm_out (optional) receives the
+ * partial_sums: scratch float64[rb_clip_adam_scratch_elems()], ZERO-INITIALISED once by the caller (its last element is a
+ * self-resetting completion ticket).  norm_out (optional) receives the
  * pre-clip global L2 norm. */
 int rb_clip_adam_scratch_elems(void);
 int rb_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t P, float grad_scale,

@@ -208,7 +208,7 @@ class Agent:
             self._streams = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
         return self._streams
 
-    def _update_fused(self, batch, target_noise=None):
+    def _update_fused(self, batch, target_noise=None, after_loss=None):
         """agent.py:66-98 with the fused head: torch only runs the conv bodies (forward x3, backward x1).
         The three network passes are independent until the loss, and every conv kernel of this size leaves most of the
         148 SMs idle, so they run as three concurrent branches (fork/join with events; inside the captured CUDA graph
@@ -251,6 +251,17 @@ class Agent:
             main.wait_event(done_tg)
             loss, dz = c51_dueling_loss_grad(z_on, z_t, self.action_space, self.atoms, actions, returns, nonterminals, weights,
                                              self.support, self.Vmin, self.Vmax, self.delta_z, self.discount ** self.n)
+            wb_done = None
+            if after_loss is not None:
+                # the priority write-back (agent.py:100) needs nothing but the per-sample losses: it runs on a side
+                # stream beside the whole backward instead of at the end of the critical path
+                loss_ready = torch.cuda.Event()
+                loss_ready.record(main)
+                with torch.cuda.stream(s_ns):
+                    s_ns.wait_event(loss_ready)
+                    after_loss(loss)
+                    wb_done = torch.cuda.Event()
+                    wb_done.record(s_ns)
             dh = torch.empty((B, 2 * on.hidden_size), dtype=torch.float32, device=self.device)
             dx = torch.empty_like(xs_d)
             if manual:
@@ -289,12 +300,15 @@ class Agent:
             x_s.backward(dx)
             self.sync.all_reduce_(self.optimiser.flat_grad)
         self.optimiser.step(grad_scale=1.0 / self.sync.world_size)
+        if wb_done is not None:
+            main.wait_event(wb_done)
         return loss
 
-    def _update_from_batch(self, batch, target_noise=None):
-        """agent.py:66-98 on an already sampled batch; returns per-sample losses (device)."""
+    def _update_from_batch(self, batch, target_noise=None, after_loss=None):
+        """agent.py:66-98 on an already sampled batch; returns per-sample losses (device).  `after_loss(loss)`, if
+        given, is called as soon as the losses exist (the fused path runs it on a side stream)."""
         if self._fused_path(batch[1].shape[0]):
-            return self._update_fused(batch, target_noise)
+            return self._update_fused(batch, target_noise, after_loss)
         idxs, states, actions, returns, next_states, nonterminals, weights = batch
         q_s = self.online_net.logits(states)
         with torch.no_grad():
@@ -310,15 +324,16 @@ class Agent:
         q_s.backward(grad)
         self.sync.all_reduce_(self.optimiser.flat_grad)
         self.optimiser.step(grad_scale=1.0 / self.sync.world_size)
+        if after_loss is not None:
+            after_loss(loss)
         return loss
 
     def _learn_eager(self, mem):
         batch = mem.sample(self.batch_size)
-        loss = self._update_from_batch(batch)
         if isinstance(mem, ReplayMemory):
-            mem.update_priorities(batch[0], loss)
-        else:  # a foreign (reference-style, host) memory: agent.py:100
-            mem.update_priorities(batch[0], loss.detach().cpu().numpy())
+            return self._update_from_batch(batch, after_loss=lambda loss: mem.update_priorities(batch[0], loss))
+        loss = self._update_from_batch(batch)
+        mem.update_priorities(batch[0], loss.detach().cpu().numpy())  # a foreign (reference-style, host) memory: agent.py:100
         return loss
 
     def _capture(self, mem):
@@ -330,8 +345,7 @@ class Agent:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             batch = mem.sample_into(ws)
-            loss = self._update_from_batch(batch)
-            mem.update_priorities(batch[0], loss)
+            loss = self._update_from_batch(batch, after_loss=lambda l: mem.update_priorities(batch[0], l))
         self._graph, self._ws, self.last_loss = graph, ws, loss
 
     GRAPH_WARMUP = 2  # eager updates before capture (cuDNN/cuBLAS plan selection, autograd buffers)

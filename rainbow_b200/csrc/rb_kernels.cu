@@ -1039,8 +1039,8 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(ADAM_THREADS)
 k_clip_adam(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ exp_avg,
             float* __restrict__ exp_avg_sq, int64_t P, float grad_scale, float max_norm, float lr, float b1, float b2,
-            float eps, const int64_t* __restrict__ step_count, const double* __restrict__ partial, int n_partial,
-            float* __restrict__ norm_out) {
+            float eps, int64_t* __restrict__ step_count, const double* __restrict__ partial, int n_partial,
+            float* __restrict__ norm_out, unsigned int* __restrict__ done_ticket) {
   __shared__ double s_red[ADAM_THREADS / 32];
   __shared__ float s_coef;
   // every CTA re-reduces the (few hundred) partial sums in the same order: deterministic, no atomics
@@ -1090,9 +1090,18 @@ k_clip_adam(float* __restrict__ param, const float* __restrict__ grad, float* __
       exp_avg_sq[i] = v;
     }
   }
+  // every CTA has read *step_count above; the last one to get here advances it (self-resetting ticket), which saves a
+  // dependent 1-thread launch on the critical path
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(done_ticket, 1u);
+    if (t == gridDim.x - 1) {
+      *done_ticket = 0u;
+      *step_count = step;
+    }
+  }
 }
-
-__global__ void k_bump_step(int64_t* step) { *step += 1; }
 
 int adam_ctas(int64_t P) {
   int64_t want = (P / 4 + ADAM_THREADS - 1) / ADAM_THREADS;
@@ -1349,7 +1358,7 @@ int rb_noisy_compose(const float* mu, const float* sigma, const float* eps, int6
   return check_launch("rb_noisy_compose");
 }
 
-int rb_clip_adam_scratch_elems(void) { return ADAM_MAX_CTAS; }
+int rb_clip_adam_scratch_elems(void) { return ADAM_MAX_CTAS + 1; }  // partial sums + one ticket word (zero-initialised by the caller)
 
 int rb_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t P, float grad_scale,
                  float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_count, double* partial_sums,
@@ -1364,11 +1373,9 @@ int rb_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg
   if (rc != RB_OK) return rc;
   { ProfScope prof_(RB_K_CLIP_ADAM, (cudaStream_t)stream);
     k_clip_adam<<<ctas, ADAM_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, P, grad_scale, max_norm, lr,
-                                                               beta1, beta2, eps, step_count, partial_sums, ctas, norm_out); }
-  rc = check_launch("rb_clip_adam");
-  if (rc != RB_OK) return rc;
-  k_bump_step<<<1, 1, 0, (cudaStream_t)stream>>>(step_count);
-  return check_launch("rb_clip_adam(step)");
+                                                               beta1, beta2, eps, step_count, partial_sums, ctas, norm_out,
+                                                               reinterpret_cast<unsigned int*>(partial_sums + ADAM_MAX_CTAS)); }
+  return check_launch("rb_clip_adam");
 }
 
 }  // extern "C"
