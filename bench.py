@@ -385,7 +385,8 @@ def ours(opts, cfg, rank, world, local):
     noisy = sum(m.weight_epsilon.numel() + m.bias_epsilon.numel() for m in agent.online_net.noisy_layers())
     alg = algorithmic_bytes(cfg, P, noisy)
     launches_per_step = {"noise_factors": 2, "tree_sample": 1, "gather": 1, "head_fc1": 2, "head_fc2": 2, "c51_dueling": 1,
-                         "head_wgrad2": 1, "head_dh": 1, "head_bwd1": 1, "sqnorm": 1, "clip_adam": 1, "tree_update": 1}
+                         "head_wgrad2": 1, "head_dh": 1, "head_bwd1": 1, "bias_grad": 3, "sqnorm": 1, "clip_adam": 1,
+                         "tree_update": 1}
     kernels = {}
     for name, (cnt, us) in kt.result.items():
         if name in alg:
@@ -419,9 +420,9 @@ def ours(opts, cfg, rank, world, local):
                     "what": f"per step: {REPLAY_FREQUENCY} x mem.append(frame from pinned host memory) + dqn.reset_noise() + dqn.learn(mem) + "
                             "per-sample loss copied to pinned host memory and read by the host one step behind the GPU (double buffer)"},
             # our kernels launched in the timed `value` region, per step: 2 k_noise_factors, k_tree_sample, k_gather,
-            # 2 x (k_head_fc<.,1> + k_head_fc<.,2>), k_c51_dueling, k_head_wgrad2, k_head_dh, k_head_bwd1, k_sqnorm, k_clip_adam,
-            # k_bump_step, k_tree_update = 16
-            "gpu_launches": K * 16,
+            # 2 x (k_head_fc<.,1> + k_head_fc<.,2>), k_c51_dueling, k_head_wgrad2, k_head_dh, k_head_bwd1, 3 k_bias_grad,
+            # k_sqnorm, k_clip_adam, k_tree_update_warp = 18 (the remaining ~19 graph nodes per step are cuDNN / ATen)
+            "gpu_launches": K * sum(launches_per_step.values()),
             "clocks": clocks, "roofline": roofline}
     if world == 1 and not opts.no_cpu_baseline:
         ups, dt, threads, n_cpu = run_cpu_port(cfg, opts.cpu_updates, 3, with_appends=True, budget_s=25)
