@@ -302,6 +302,9 @@ def ours(opts, cfg, rank, world, local):
         step()
     mem.check_last_sample()
     log("warm-up + graph capture done")
+    if world > 1:
+        import faulthandler
+        faulthandler.cancel_dump_traceback_later()
 
     if opts.profile_steps:   # ncu window (use with `ncu --profile-from-start off`): numbers under a profiler are never reported
         mode = opts.profile_mode
@@ -479,6 +482,10 @@ def main():
         reference_arm(opts, cfg, rank)
         return
     if world > 1:
+        # a communicator that never comes up must not eat the caller's whole time budget: dump every thread's stack and
+        # exit if set-up + warm-up of the multi-rank job take longer than this (cancelled once the timed regions start)
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("RB_BENCH_SETUP_TIMEOUT", "300")), exit=True, file=sys.stderr)
         from rainbow_b200.dist import init_from_env
         init_from_env("nccl")
     elif opts.gpus > 1:
