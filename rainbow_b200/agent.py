@@ -354,9 +354,11 @@ class Agent:
         """agent.py:61-100.  Exactly one update per call: the first GRAPH_WARMUP calls run eagerly on a side
         stream (torch's documented warm-up recipe for whole-step capture), the next call captures the graph and
         every call from then on is one graph launch."""
-        graphable = (self.use_cuda_graph and isinstance(mem, ReplayMemory) and mem.rng == "philox")
-        key = (id(mem), self.batch_size)
-        if graphable and self._graph_key != key:
+        # the captured graph bakes in: this memory's buffers, the batch size and training-mode (noisy) weights
+        graphable = (self.use_cuda_graph and isinstance(mem, ReplayMemory) and mem.rng == "philox" and
+                     self.online_net.training)
+        key = (mem, self.batch_size)   # holds a reference: a recycled id() can never alias a dead memory's graph
+        if graphable and (self._graph_key is None or self._graph_key[0] is not mem or self._graph_key[1] != self.batch_size):
             self._graph, self._graph_key, self._warm = None, key, 0
         if not graphable:
             self.last_loss = self._learn_eager(mem)

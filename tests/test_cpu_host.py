@@ -191,3 +191,29 @@ def test_bench_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "1"], capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bench_algorithmic_bytes_match_survey():
+    """The roofline numerators bench.py uses are SURVEY.md 8(d)'s per-update figures."""
+    sys.path.insert(0, ROOT)
+    import bench
+    P, noisy = 6_868_928, 3_395_429
+    c2 = bench.algorithmic_bytes(bench.CONFIGS["C2"], P, noisy)
+    assert c2["tree_sample"] == 3328 and c2["gather"] == 8_807_840 and c2["c51"] == 157_772 and c2["tree_update"] == 8192
+    assert c2["clip_adam"] == 7 * P * 4 and c2["sqnorm"] == P * 4 and c2["noisy_resample"] == noisy * 4
+    c3 = bench.algorithmic_bytes(bench.CONFIGS["C3"], 828_842, 387_173)
+    assert c3["tree_sample"] == 2944 and c3["gather"] == 9_037_984 and c3["tree_update"] == 7040
+    c4 = bench.algorithmic_bytes(bench.CONFIGS["C4"], P, noisy)
+    assert c4["tree_sample"] == 53_248 and c4["gather"] == 140_925_440 and c4["c51"] == 2_521_292 and c4["tree_update"] == 131_072
+    assert bench.host_threads() >= 1
+
+
+def test_stdout_guard_keeps_library_prints_off_stdout(tmp_path):
+    """Only the JSON line may reach fd 1 (NCCL prints its banner there)."""
+    script = tmp_path / "guard.py"
+    script.write_text("import os, sys\nsys.path.insert(0, %r)\nimport bench\nbench.GUARD = bench.StdoutGuard()\n"
+                      "os.write(1, b'library banner\\n')\nprint('python print')\nbench.emit({'ok': 1})\n" % ROOT)
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout == '{"ok": 1}\n'
+    assert "library banner" in out.stderr and "python print" in out.stderr
