@@ -217,3 +217,34 @@ def test_stdout_guard_keeps_library_prints_off_stdout(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout == '{"ok": 1}\n'
     assert "library banner" in out.stderr and "python print" in out.stderr
+
+
+def test_flat_parameter_layout():
+    """FusedClipAdam host logic (no kernel is launched): every parameter becomes a view of ONE flat buffer on a
+    256-byte boundary, gradients likewise, conv parameters come first (conv_end), padding stays zero."""
+    from rainbow_b200.agent import FusedClipAdam
+    from rainbow_b200.model import DQN
+    torch.manual_seed(0)
+    net = DQN(make_args(architecture="data-efficient", hidden_size=64), 3)
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    opt = FusedClipAdam(net, lr=1e-4, eps=1e-4, max_norm=10.0)
+    named = [(n, p) for n, p in net.named_parameters()]
+    assert len(named) == 4 + 16 and opt.numel % 64 == 0
+    base = opt.flat_param.data_ptr()
+    prev_end = 0
+    for (n, p), off in zip(named, opt.offsets):
+        assert off % 64 == 0 and off >= prev_end
+        assert p.data_ptr() == base + 4 * off and p.grad.data_ptr() == opt.flat_grad.data_ptr() + 4 * off
+        assert torch.equal(p, before[n]), n                      # values survived the re-pointing
+        assert not opt.flat_param[prev_end:off].any()             # alignment padding is zero
+        prev_end = off + p.numel()
+    first_fc = next(off for (n, _), off in zip(named, opt.offsets) if n.startswith("fc_"))
+    assert opt.conv_end == first_fc and all(n.startswith("convs.") for (n, _), off in zip(named, opt.offsets) if off < first_fc)
+    opt.flat_grad.fill_(1.0)
+    opt.zero_conv_grad()
+    assert not opt.flat_grad[:opt.conv_end].any() and opt.flat_grad[opt.conv_end:].all()
+    opt.zero_grad()
+    assert not opt.flat_grad.any()
+    # load_state_dict writes through the views (the flat buffer follows), as update_target_net / --model rely on
+    net.load_state_dict({k: v + 1 for k, v in before.items()})
+    assert torch.equal(opt.flat_param[opt.offsets[0]:opt.offsets[0] + named[0][1].numel()], (before[named[0][0]] + 1).reshape(-1))
