@@ -1147,6 +1147,7 @@ int rb_tree_update(float* tree, int64_t tree_start, int64_t size, const int64_t*
                    float omega, int omega_is_applied, int B, float* running_max, int32_t* status, rb_stream_t stream) {
   if (!tree || !tree_idx || !raw_priority || !running_max) return fail(RB_ERR_INVAL, "rb_tree_update: null pointer");
   if (B <= 0 || size <= 0 || (size & 1)) return fail(RB_ERR_INVAL, "rb_tree_update: B > 0 and an even size are required");
+  if (tree_start + size > ((int64_t)1 << 31)) return fail(RB_ERR_RANGE, "rb_tree_update: tree larger than 2^31 nodes");
   { ProfScope prof_(RB_K_TREE_UPDATE, (cudaStream_t)stream);
     if (B <= 32 && tree_depth(tree_start) <= 30)
       k_tree_update_warp<<<1, 32, 0, (cudaStream_t)stream>>>(tree, tree_start, size, tree_idx, raw_priority, omega,
@@ -1229,6 +1230,7 @@ int rb_append(float* tree, int64_t tree_start, int64_t size, uint8_t* frames, in
   if (!tree || !frames || !timestep || !action || !reward || !nonterminal || !ring_state || !running_max || !state_last_frame)
     return fail(RB_ERR_INVAL, "rb_append: null pointer");
   if (size <= 0 || (size & 1)) return fail(RB_ERR_INVAL, "rb_append: an even size is required");
+  if (tree_depth(tree_start) > 32) return fail(RB_ERR_RANGE, "rb_append: tree deeper than 32 levels");  // one lane per level
   if (((uintptr_t)state_last_frame & 15) != 0) return fail(RB_ERR_INVAL, "rb_append: state_last_frame must be 16-byte aligned");
   { ProfScope prof_(RB_K_APPEND, (cudaStream_t)stream);
     k_append<<<1, APPEND_THREADS, 0, (cudaStream_t)stream>>>(tree, tree_start, size, frames, timestep, action, reward,
