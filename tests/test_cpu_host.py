@@ -167,6 +167,16 @@ p -= 0.1 * avg
 chk = p.clone()
 torch.distributed.all_reduce(chk, op=torch.distributed.ReduceOp.MAX)
 assert torch.equal(chk, p), "ranks diverged"
+# the learner reduces the flat gradient in two slices (noisy head first, on a side stream; conv slice afterwards):
+# in-place all-reduce on VIEWS of one flat buffer must equal one all-reduce of the whole buffer
+torch.manual_seed(100 + rank)
+flat = torch.randn(4096)
+whole = flat.clone()
+conv_end = 1280
+sync.all_reduce_(flat[conv_end:])
+sync.all_reduce_(flat[:conv_end])
+sync.all_reduce_(whole)
+assert torch.equal(flat, whole)
 t = torch.tensor([float(rank)])
 assert float(sync.max_(t)) == 1.0
 torch.distributed.destroy_process_group()
