@@ -55,6 +55,7 @@ extern "C" {
 #define RB_MAX_WINDOW 64         /* history + multi_step */
 #define RB_MAX_ATOMS 128
 #define RB_MAX_NOISY_LAYERS 8
+#define RB_APPEND_BATCH 8        /* transitions per rb_append_batch launch */
 
 /* status word layout written by rb_tree_sample: status[0] = 1 if the batch now in the
  * output buffers passed the whole-batch validity test, 0 otherwise; status[1] = draws used. */
@@ -128,6 +129,15 @@ int rb_append(float* tree, int64_t tree_start, int64_t size, uint8_t* frames, in
               float* reward, uint8_t* nonterminal, int64_t* ring_state, float* running_max,
               const float* state_last_frame, int32_t action_value, float reward_value, int terminal,
               rb_stream_t stream);
+
+/* k consecutive rb_append calls in ONE launch (actor side batching): HOST arrays of length k --
+ * last_frames[j] points at the j-th newest frame (float32[84*84], DEVICE memory or PINNED HOST memory, read in place),
+ * actions / rewards / terminals its fields.  Result is identical to k rb_append calls in order.  1 <= k <= RB_APPEND_BATCH.
+ * [round-1 status: compiled, not yet exercised on hardware -- ReplayMemory(defer_appends=True) is off by default] */
+int rb_append_batch(float* tree, int64_t tree_start, int64_t size, uint8_t* frames, int32_t* timestep, int32_t* action,
+                    float* reward, uint8_t* nonterminal, int64_t* ring_state, float* running_max,
+                    const float* const* last_frames, const int32_t* actions, const float* rewards, const int32_t* terminals,
+                    int k, rb_stream_t stream);
 
 /* agent.py:66-96 Agent.learn minus the three network bodies, given PRE-softmax logits [B,A,Z]
  * (model.py:75 `q`; the softmax / log_softmax of model.py:76-79 are folded in):

@@ -340,6 +340,7 @@ class Agent:
         """Record one whole update (sample -> ... -> priority write-back) into a CUDA graph.  Capturing does
         not execute; the caller replays."""
         ws = _SampleWorkspace(self.batch_size, mem.history, self.device)
+        mem.flush_appends()
         mem.push_beta()  # outside the capture: a captured fill_ would freeze beta at today's value
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
@@ -372,6 +373,7 @@ class Agent:
         else:
             if self._graph is None:
                 self._capture(mem)
+            mem.flush_appends()   # no-op unless the memory defers its appends
             mem.push_beta()
             self._graph.replay()
         self._learn_calls += 1

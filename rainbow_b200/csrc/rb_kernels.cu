@@ -584,6 +584,104 @@ k_append(float* tree, int64_t tree_start, int64_t size, uint8_t* __restrict__ fr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K5b  append_batch : up to RB_APPEND_BATCH queued transitions in ONE launch (actor side).
+// ------------------------------------------------------------------------------------------------
+// Equivalent to calling k_append k times in order: the records go to slots head, head+1, ... (mod size), the
+// in-episode counter follows the terminals, every new leaf gets the running max (which appends never change) and,
+// because every internal node is recomputed from its children, the tree after k sequential walks equals the tree
+// after ONE level-synchronous batched walk over the k leaves (same argument as for rb_tree_update).  The frame
+// pointers may be device memory or pinned host memory (read in place over PCIe: no staging copy, no extra launch).
+struct AppendBatch {
+  const float* frame[RB_APPEND_BATCH];
+  int32_t action[RB_APPEND_BATCH];
+  float reward[RB_APPEND_BATCH];
+  int32_t terminal[RB_APPEND_BATCH];
+  int k;
+};
+
+__global__ void __launch_bounds__(APPEND_THREADS)
+k_append_batch(float* tree, int64_t tree_start, int64_t size, uint8_t* __restrict__ frames, int32_t* timestep,
+               int32_t* action, float* reward, uint8_t* nonterminal, int64_t* ring_state, const float* running_max,
+               const __grid_constant__ AppendBatch ab) {
+  const int tid = threadIdx.x;
+  const int64_t head = ring_state[0];
+  const int64_t t_ep0 = ring_state[2];
+  const int k = ab.k;
+  for (int j = 0; j < k; ++j) {  // frames: f32 * 255 then truncating cast (memory.py:106)
+    int64_t slot = head + j;
+    if (slot >= size) slot -= size;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(frames + (size_t)slot * RB_FRAME_BYTES);
+    const float4* src = reinterpret_cast<const float4*>(ab.frame[j]);
+    for (int v = tid; v < RB_FRAME_BYTES / 4; v += APPEND_THREADS) {
+      const float4 x = src[v];
+      const uint32_t a = (uint32_t)(uint8_t)(int)__fmul_rn(x.x, 255.0f);
+      const uint32_t b = (uint32_t)(uint8_t)(int)__fmul_rn(x.y, 255.0f);
+      const uint32_t c = (uint32_t)(uint8_t)(int)__fmul_rn(x.z, 255.0f);
+      const uint32_t d = (uint32_t)(uint8_t)(int)__fmul_rn(x.w, 255.0f);
+      dst[v] = a | (b << 8) | (c << 16) | (d << 24);
+    }
+  }
+  if (tid < 32) {
+    const unsigned full = 0xffffffffu;
+    const int lane = tid;
+    const int L = tree_depth(tree_start);
+    const bool active = lane < k;
+    int64_t slot = head + lane;
+    if (slot >= size) slot -= size;
+    int64_t node = active ? slot + tree_start : -1;
+    float val = *running_max;  // memory.py:107
+    if (active) {              // record fields; timestep follows the terminals of the earlier queued transitions
+      int64_t t = t_ep0;
+      for (int i = 0; i < lane; ++i) t = ab.terminal[i] ? 0 : t + 1;
+      timestep[slot] = (int32_t)t;
+      action[slot] = ab.action[lane];
+      reward[slot] = ab.reward[lane];
+      nonterminal[slot] = ab.terminal[lane] ? 0 : 1;
+    }
+    float sib[32];
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      sib[l] = 0.0f;
+      if (l < L && active) {
+        const int64_t nl = ((node + 1) >> l) - 1;
+        const int64_t sn = (nl & 1) ? nl + 1 : nl - 1;
+        sib[l] = __ldcg(tree + sn);
+      }
+    }
+    if (active) __stcg(tree + node, val);  // k distinct leaves (k <= size is checked by the launcher)
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      if (l < L) {
+        const int64_t parent = active ? ((node - 1) >> 1) : -(int64_t)(lane + 1);
+        const bool is_left = active && (node & 1);
+        const unsigned grp = __match_any_sync(full, (int)parent);
+        const unsigned lefts = __ballot_sync(full, is_left);
+        const unsigned other = grp & (is_left ? ~lefts : lefts);
+        const float partner = __shfl_sync(full, val, other ? __ffs(other) - 1 : lane);
+        val = __fadd_rn(val, other ? partner : sib[l]);
+        node = parent;
+        if (active && lane == __ffs(grp) - 1) __stcg(tree + node, val);
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int64_t nh = head + k;
+    bool wrapped = false;
+    if (nh >= size) {
+      nh -= size;
+      wrapped = true;
+    }
+    int64_t t = t_ep0;
+    for (int i = 0; i < k; ++i) t = ab.terminal[i] ? 0 : t + 1;
+    ring_state[0] = nh;
+    if (wrapped) ring_state[1] = 1;
+    ring_state[2] = t;
+    ring_state[3] = ring_state[3] + k;
+  }
+}
+
 // ================================================================================================
 // K3  c51_loss_grad : double-DQN argmax + categorical projection + IS-weighted CE loss + gradient.
 // ================================================================================================
@@ -1237,6 +1335,32 @@ int rb_append(float* tree, int64_t tree_start, int64_t size, uint8_t* frames, in
                                                            nonterminal, ring_state, running_max, state_last_frame,
                                                            action_value, reward_value, terminal); }
   return check_launch("rb_append");
+}
+
+int rb_append_batch(float* tree, int64_t tree_start, int64_t size, uint8_t* frames, int32_t* timestep, int32_t* action,
+                    float* reward, uint8_t* nonterminal, int64_t* ring_state, float* running_max,
+                    const float* const* last_frames, const int32_t* actions, const float* rewards, const int32_t* terminals,
+                    int k, rb_stream_t stream) {
+  if (!tree || !frames || !timestep || !action || !reward || !nonterminal || !ring_state || !running_max || !last_frames ||
+      !actions || !rewards || !terminals)
+    return fail(RB_ERR_INVAL, "rb_append_batch: null pointer");
+  if (size <= 0 || (size & 1)) return fail(RB_ERR_INVAL, "rb_append_batch: an even size is required");
+  if (k <= 0 || k > RB_APPEND_BATCH || k > size) return fail(RB_ERR_RANGE, "rb_append_batch: 1 <= k <= RB_APPEND_BATCH (and k <= size)");
+  if (tree_depth(tree_start) > 30) return fail(RB_ERR_RANGE, "rb_append_batch: tree deeper than 30 levels");
+  AppendBatch ab;
+  memset(&ab, 0, sizeof(ab));
+  ab.k = k;
+  for (int j = 0; j < k; ++j) {
+    if (!last_frames[j] || ((uintptr_t)last_frames[j] & 15)) return fail(RB_ERR_INVAL, "rb_append_batch: frames must be non-null and 16-byte aligned");
+    ab.frame[j] = last_frames[j];
+    ab.action[j] = actions[j];
+    ab.reward[j] = rewards[j];
+    ab.terminal[j] = terminals[j] ? 1 : 0;
+  }
+  { ProfScope prof_(RB_K_APPEND, (cudaStream_t)stream);
+    k_append_batch<<<1, APPEND_THREADS, 0, (cudaStream_t)stream>>>(tree, tree_start, size, frames, timestep, action, reward,
+                                                                   nonterminal, ring_state, running_max, ab); }
+  return check_launch("rb_append_batch");
 }
 
 int rb_c51_loss_grad(const float* q_online_s, const float* q_online_ns, const float* q_target_ns, const int64_t* actions,

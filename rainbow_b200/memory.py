@@ -198,7 +198,9 @@ class ReplayMemory:
     strict (read the kernel's status word after every sample and raise if the batch was rejected
     max_attempts times -- costs a device synchronisation)."""
 
-    def __init__(self, args, capacity, rng="philox", seed=None, max_attempts=64, strict=False):
+    APPEND_BATCH = 8  # RB_APPEND_BATCH
+
+    def __init__(self, args, capacity, rng="philox", seed=None, max_attempts=64, strict=False, defer_appends=False):
         self.device = _require_cuda(args.device)
         self.capacity = int(capacity)
         self.history = int(args.history_length)
@@ -213,6 +215,12 @@ class ReplayMemory:
         self.rng = rng
         self.max_attempts = int(max_attempts)
         self.strict = bool(strict)
+        # defer_appends: append() only queues (frame reference + fields); the queue is written by ONE rb_append_batch
+        # launch before the next read of the replay (sample / update_priorities / iteration / pickling) or when it holds
+        # APPEND_BATCH transitions.  The caller must not modify a queued frame tensor before the flush.
+        # [round-1 status: off by default, not yet exercised on hardware]
+        self.defer_appends = bool(defer_appends)
+        self._queue = []
         self.t = 0  # in-episode step of the next append (memory.py:100); device copy in ring_state[2]
         # memory.py:101: [gamma**i] in Python doubles, then float32
         self.n_step_scaling = torch.tensor([self.discount ** i for i in range(self.n)], dtype=torch.float32,
@@ -238,6 +246,18 @@ class ReplayMemory:
         """memory.py:105-108.  `state` is the float32 [history,84,84] frame stack in [0,1]; only the newest
         frame is stored (quantised to uint8 on the device)."""
         last = state[-1]
+        if self.defer_appends and (last.is_cuda or last.is_pinned()):
+            last = last.to(torch.float32).contiguous()
+            if last.data_ptr() % 16:
+                last = last.clone()
+            self._queue.append((last, int(action), float(reward), bool(terminal)))
+            tr = self.transitions
+            tr.index = (tr.index + 1) % tr.size       # host mirrors advance now, the device copy at the flush
+            tr.full = tr.full or tr.index == 0
+            self.t = 0 if terminal else self.t + 1
+            if len(self._queue) >= self.APPEND_BATCH:
+                self.flush_appends()
+            return
         if not last.is_cuda:
             last = last.to(self.device, non_blocking=True)
         last = last.to(torch.float32).contiguous()
@@ -245,6 +265,24 @@ class ReplayMemory:
             last = last.clone()
         self.transitions.append_frame(last, action, reward, terminal)
         self.t = 0 if terminal else self.t + 1
+
+    def flush_appends(self):
+        """Write the queued transitions (defer_appends=True) with one rb_append_batch launch."""
+        if not self._queue:
+            return
+        import ctypes as C
+        q, self._queue = self._queue, []
+        k = len(q)
+        tr = self.transitions
+        frames = (C.c_void_p * k)(*[f.data_ptr() for f, _, _, _ in q])   # device or pinned-host pointers (UVA)
+        acts = (C.c_int32 * k)(*[a for _, a, _, _ in q])
+        rews = (C.c_float * k)(*[r for _, _, r, _ in q])
+        terms = (C.c_int32 * k)(*[1 if t else 0 for _, _, _, t in q])
+        _lib.check(self._lib.rb_append_batch(
+            _lib.ptr(tr.tree), tr.tree_start, tr.size, _lib.ptr(tr.frames), _lib.ptr(tr.timestep), _lib.ptr(tr.action),
+            _lib.ptr(tr.reward), _lib.ptr(tr.nonterminal), _lib.ptr(tr.ring_state), _lib.ptr(tr.running_max), frames, acts,
+            rews, terms, k, _lib.stream()))
+        self._flushed_refs = q   # keep the frames alive until the next flush (the launch is asynchronous)
 
     # ---- sample --------------------------------------------------------------------------------
     def _launch_sample(self, ws, u01=None, attempts=0):
@@ -266,7 +304,7 @@ class ReplayMemory:
 
     def sample_into(self, ws):
         """Device-RNG sample into caller-owned buffers: two launches, no synchronisation (graph capturable).
-        The caller is responsible for push_beta() (outside any graph capture)."""
+        The caller is responsible for push_beta() and flush_appends() (outside any graph capture)."""
         self._launch_sample(ws)
         self._launch_gather(ws)
         self._last = ws
@@ -276,6 +314,7 @@ class ReplayMemory:
         """memory.py:148-155.  Returns (tree_idxs, states, actions, returns, next_states, nonterminals, weights),
         all device tensors (the reference returns tree_idxs as numpy; update_priorities takes either)."""
         ws = _SampleWorkspace(int(batch_size), self.history, self.device)
+        self.flush_appends()
         self.push_beta()
         if self.rng == "numpy":
             # consume the legacy global generator exactly like np.random.uniform(0, seg, [B]) does
@@ -304,12 +343,15 @@ class ReplayMemory:
     # ---- priorities ----------------------------------------------------------------------------
     def update_priorities(self, idxs, priorities):
         """memory.py:157-159: raw per-sample losses -> ^omega -> leaves -> propagate to the root."""
+        if self._queue and not torch.cuda.is_current_stream_capturing():
+            self.flush_appends()
         self.transitions.update(idxs, priorities, omega=self.priority_exponent)
 
     # ---- validation iterator (memory.py:162-180) -------------------------------------------------
     _ITER_CHUNK = 64
 
     def __iter__(self):
+        self.flush_appends()
         self.current_idx = 0
         self._iter_buf = None
         self._iter_base = 0
@@ -333,6 +375,7 @@ class ReplayMemory:
 
     # ---- pickling (main.py:85-100 pickles the whole object) --------------------------------------
     def __getstate__(self):
+        self.flush_appends()
         tr = self.transitions
         return dict(
             version=1, capacity=self.capacity, history=self.history, discount=self.discount, n=self.n,
@@ -353,6 +396,7 @@ class ReplayMemory:
         self.transitions = SegmentTree(self.capacity, self.device)
         self.transitions.load_arrays(s["sum_tree"], s["frames"], s["timestep"], s["action"], s["reward"],
                                      s["nonterminal"], s["index"], s["full"], s["t"], s["max"])
+        self.defer_appends, self._queue = False, []
         self._rng_counter = torch.tensor([s["rng_counter"]], dtype=torch.int64, device=self.device)
         self._beta_dev = torch.full((1,), float(self.priority_weight), dtype=torch.float32, device=self.device)
         self._beta_pushed = float(self.priority_weight)
