@@ -258,6 +258,8 @@ class ReplayMemory:
             if len(self._queue) >= self.APPEND_BATCH:
                 self.flush_appends()
             return
+        if self._queue:   # a frame that cannot be queued (pageable host memory) must not overtake queued ones
+            self.flush_appends_keep_mirrors()
         if not last.is_cuda:
             last = last.to(self.device, non_blocking=True)
         last = last.to(torch.float32).contiguous()
@@ -265,6 +267,9 @@ class ReplayMemory:
             last = last.clone()
         self.transitions.append_frame(last, action, reward, terminal)
         self.t = 0 if terminal else self.t + 1
+
+    def flush_appends_keep_mirrors(self):
+        self.flush_appends()
 
     def flush_appends(self):
         """Write the queued transitions (defer_appends=True) with one rb_append_batch launch."""
