@@ -259,7 +259,7 @@ class ReplayMemory:
                 self.flush_appends()
             return
         if self._queue:   # a frame that cannot be queued (pageable host memory) must not overtake queued ones
-            self.flush_appends_keep_mirrors()
+            self.flush_appends()
         if not last.is_cuda:
             last = last.to(self.device, non_blocking=True)
         last = last.to(torch.float32).contiguous()
@@ -267,9 +267,6 @@ class ReplayMemory:
             last = last.clone()
         self.transitions.append_frame(last, action, reward, terminal)
         self.t = 0 if terminal else self.t + 1
-
-    def flush_appends_keep_mirrors(self):
-        self.flush_appends()
 
     def flush_appends(self):
         """Write the queued transitions (defer_appends=True) with one rb_append_batch launch."""
