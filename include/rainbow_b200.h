@@ -55,6 +55,7 @@ extern "C" {
 #define RB_MAX_WINDOW 64         /* history + multi_step */
 #define RB_MAX_ATOMS 128
 #define RB_MAX_NOISY_LAYERS 8
+#define RB_MAX_PEERS 8           /* ranks of one NVLink domain handled by rb_peer_clip_adam */
 #define RB_APPEND_BATCH 8        /* transitions per rb_append_batch launch */
 
 /* status word layout written by rb_tree_sample: status[0] = 1 if the batch now in the
@@ -252,6 +253,21 @@ int rb_clip_adam_scratch_elems(void);
 int rb_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t P, float grad_scale,
                  float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_count,
                  double* partial_sums, float* norm_out, rb_stream_t stream);
+
+/* Multi-GPU replacement of "all-reduce the flat gradient, then rb_clip_adam on every rank" (agent.py:97-98 under data
+ * parallelism; no reference counterpart): reduce-scatter by peer loads + clip + Adam on the owned 1/world slice (moments
+ * sharded) + all-gather by peer stores, ordered by epoch flags in peer-visible memory.  HOST arrays of length `world`:
+ * peer_grad[q] / peer_param[q] = rank q's flat gradient / parameter buffer (P floats, P % (4*world) == 0),
+ * peer_flags[q] = rank q's uint64[3*world] flag block, peer_norms[q] = rank q's double[world] block (both zero-initialised
+ * once), all mapped on this device.  gred: float32[P/world] scratch; exp_avg / exp_avg_sq: float32[P/world] (this rank's
+ * shard); epoch: device uint64 (zero-initialised, advanced by the call); scratch: rb_peer_scratch_bytes() zeroed bytes.
+ * grad_scale multiplies the reduced gradient (1/world for averaging).  Every rank must make the same call each step.
+ * [round-1 status: compiled, not yet exercised on hardware] */
+int rb_peer_scratch_bytes(void);
+int rb_peer_clip_adam(const float* const* peer_grad, float* const* peer_param, uint64_t* const* peer_flags,
+                      double* const* peer_norms, int world, int rank, int64_t P, float* gred, float* exp_avg,
+                      float* exp_avg_sq, float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps,
+                      int64_t* step_count, uint64_t* epoch, void* scratch, float* norm_out, rb_stream_t stream);
 
 #ifdef __cplusplus
 }

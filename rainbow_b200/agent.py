@@ -66,7 +66,7 @@ class FusedClipAdam:
 
     ALIGN = 64  # elements
 
-    def __init__(self, net, lr, eps, max_norm, betas=(0.9, 0.999)):
+    def __init__(self, net, lr, eps, max_norm, betas=(0.9, 0.999), peer=False):
         named = [(n, p) for n, p in net.named_parameters() if p.requires_grad]
         self.params = [p for _, p in named]
         dev = self.params[0].device
@@ -81,12 +81,20 @@ class FusedClipAdam:
         if self.conv_end is None:
             self.conv_end = off
         self.lr, self.eps, self.max_norm, self.betas = float(lr), float(eps), float(max_norm), betas
-        self.flat_param = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.flat_grad = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.exp_avg = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.peer = None
+        if peer:   # [round-1 status: untested on hardware] buffers in symmetric memory, optimiser fused with the exchange
+            from .peer import PeerOptimizerState
+            self.peer = PeerOptimizerState(off, dev)
+            self.numel = off = self.peer.numel
+            self.flat_param, self.flat_grad = self.peer.flat_param, self.peer.flat_grad
+            self.exp_avg, self.exp_avg_sq = self.peer.exp_avg, self.peer.exp_avg_sq
+        else:
+            self.flat_param = torch.zeros(off, dtype=torch.float32, device=dev)
+            self.flat_grad = torch.zeros(off, dtype=torch.float32, device=dev)
+            self.exp_avg = torch.zeros(off, dtype=torch.float32, device=dev)
+            self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.step_count = self.peer.step_count if self.peer is not None else torch.zeros(1, dtype=torch.int64, device=dev)
+        self.grad_norm = self.peer.grad_norm if self.peer is not None else torch.zeros(1, dtype=torch.float32, device=dev)
         self._lib = _lib.load()
         self._partial = torch.zeros(self._lib.rb_clip_adam_scratch_elems(), dtype=torch.float64, device=dev)
         with torch.no_grad():
@@ -104,6 +112,9 @@ class FusedClipAdam:
         self.flat_grad[:self.conv_end].zero_()
 
     def step(self, grad_scale=1.0):
+        if self.peer is not None:   # reduce-scatter + clip + Adam + all-gather over peer memory (1/world folded in)
+            self.peer.step(self.max_norm, self.lr, self.betas, self.eps)
+            return
         _lib.check(self._lib.rb_clip_adam(
             _lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
             self.numel, float(grad_scale), self.max_norm, self.lr, self.betas[0], self.betas[1], self.eps,
@@ -155,8 +166,12 @@ class Agent:
         self.online_net.noise_seed = (self.online_net.noise_seed * 2 + 1 + 7919 * self.sync.rank) & (2 ** 63 - 1)
         self.target_net.noise_seed = (self.target_net.noise_seed * 2 + 2 + 7919 * self.sync.rank) & (2 ** 63 - 1)
 
-        self.optimiser = FusedClipAdam(self.online_net, lr=args.learning_rate, eps=args.adam_eps, max_norm=self.norm_clip)
+        self.peer_optimizer = bool(getattr(args, "peer_optimizer", False)) and self.sync.enabled
+        self.optimiser = FusedClipAdam(self.online_net, lr=args.learning_rate, eps=args.adam_eps, max_norm=self.norm_clip,
+                                       peer=self.peer_optimizer)
         self.sync.broadcast_(self.optimiser.flat_param)  # identical initial parameters on every rank
+        if self.peer_optimizer:
+            self.sync.exchange = False   # the optimiser step does the gradient exchange itself
         self.update_target_net()
         self.target_net.train()
         for p in self.target_net.parameters():

@@ -46,10 +46,11 @@ class GradSync:
         self.enabled = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.world_size = dist.get_world_size(group) if self.enabled else 1
         self.rank = dist.get_rank(group) if self.enabled else 0
+        self.exchange = True   # False: somebody else (the peer-memory optimiser) moves the gradients
 
     def all_reduce_(self, flat_grad):
         """In-place SUM over ranks of the flat gradient buffer (one collective per update)."""
-        if self.enabled:
+        if self.enabled and self.exchange:
             dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=self.group)
         return flat_grad
 
