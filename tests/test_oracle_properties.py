@@ -87,3 +87,70 @@ def test_c51_projection_conserves_mass(seed, A, B):
         nz = np.flatnonzero(m[i])
         assert 1 <= nz.size <= 2 and nz.max() - nz.min() <= 1
         assert abs(nz.mean() - b) <= 1.0 + 1e-3
+
+
+def _warp_walk(tree, ts, leaves, values):
+    """numpy emulation of the register algorithm of k_tree_update_warp / k_append_batch: every lane prefetches the
+    siblings of its path BEFORE anything is written, lanes that share a parent take the sibling value from the partner
+    lane if the sibling is itself being updated, the lowest lane of a group writes."""
+    L = int(np.log2(ts + 1))
+    lanes = len(leaves)
+    # duplicates: highest lane wins
+    val = np.array(values, np.float32)
+    for i in range(lanes):
+        same = [j for j in range(lanes) if leaves[j] == leaves[i]]
+        val[i] = np.float32(values[max(same)])
+    sib = np.zeros((lanes, L), np.float32)
+    for i in range(lanes):
+        for l in range(L):
+            nl = ((leaves[i] + 1) >> l) - 1
+            sn = nl + 1 if nl & 1 else nl - 1
+            sib[i, l] = tree[sn]
+    node = np.array(leaves, np.int64)
+    for i in range(lanes):
+        tree[node[i]] = val[i]
+    for l in range(L):
+        parent = (node - 1) >> 1
+        is_left = (node & 1) == 1
+        new = val.copy()
+        for i in range(lanes):
+            other = [j for j in range(lanes) if parent[j] == parent[i] and is_left[j] != is_left[i]]
+            sv = val[min(other)] if other else sib[i, l]
+            new[i] = np.float32(val[i] + sv)
+        val, node = new, parent
+        for i in range(lanes):
+            tree[node[i]] = val[i]
+    return tree
+
+
+@settings(max_examples=60, deadline=None)
+@given(half=st.integers(2, 200), seed=st.integers(0, 2 ** 31 - 1), k=st.integers(1, 8), start=st.integers(0, 10 ** 6))
+def test_batched_walk_equals_sequential_appends(half, seed, k, start):
+    """The claim behind rb_append_batch: k sequential single-leaf walks (memory.py:36-41) leave the same float32 tree as
+    ONE batched walk over the k (consecutive, wrapping) leaves -- and the same for arbitrary leaf sets with duplicates
+    (rb_tree_update's single-warp path)."""
+    cap = 2 * half
+    k = min(k, cap)
+    rs = np.random.RandomState(seed)
+    t = oracle.OracleTree(cap, with_data=False)
+    ts = t.tree_start
+    t.update(np.arange(cap) + ts, rs.uniform(0, 3, cap).astype(np.float32))
+    vmax = np.float32(t.max[0])
+    head = start % cap
+    seq = t.sum_tree.copy()
+    for j in range(k):                                   # k sequential appends of the running max
+        oracle.lib().orc_tree_set_leaf(seq, ts + (head + j) % cap, float(vmax))
+    leaves = [ts + (head + j) % cap for j in range(k)]
+    bat = _warp_walk(t.sum_tree.copy(), ts, leaves, [vmax] * k)
+    assert np.array_equal(bat, seq)
+    # arbitrary update batch with duplicates vs the oracle's level-synchronous update
+    B = int(rs.randint(1, 33))
+    idx = (rs.randint(0, cap, B) + ts).tolist()
+    if B > 2:
+        idx[-1] = idx[0]
+    vals = rs.uniform(0, 4, B).astype(np.float32)
+    ref = oracle.OracleTree(cap, with_data=False)
+    ref.sum_tree[:] = t.sum_tree
+    ref.update(np.array(idx, np.int64), vals)
+    got = _warp_walk(t.sum_tree.copy(), ts, idx, vals.tolist())
+    assert np.array_equal(got, ref.sum_tree)
