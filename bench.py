@@ -85,7 +85,7 @@ def host_threads():
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed regions run."""
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=0.02):
         super().__init__(daemon=True)
         self.index, self.period, self.samples, self.reasons, self.max_mhz, self.ok = index, period, [], set(), None, False
         self._stop_evt = threading.Event()
