@@ -40,8 +40,8 @@ ACTIONS = 6
 REPLAY_FREQUENCY = 4  # main.py:37 -- env steps (appends) per learner update in the e2e loop
 
 
-def make_args(cfg, device):
-    return argparse.Namespace(device=device, history_length=4, discount=0.99, multi_step=cfg["n"], priority_weight=0.4,
+def make_args(cfg, device, peer_optimizer=False):
+    return argparse.Namespace(peer_optimizer=peer_optimizer, device=device, history_length=4, discount=0.99, multi_step=cfg["n"], priority_weight=0.4,
                               priority_exponent=0.5, atoms=51, V_min=-10.0, V_max=10.0, batch_size=cfg["B"],
                               norm_clip=10.0, model=None, learning_rate=6.25e-5, adam_eps=1.5e-4,
                               architecture=cfg["arch"], hidden_size=cfg["hidden"], noisy_std=0.1, cuda_graph=True)
@@ -253,7 +253,7 @@ def ours(opts, cfg, rank, world, local):
     torch.cuda.set_device(dev)
     torch.manual_seed(shard_seed(0, rank))
     np.random.seed(123 + rank)
-    args = make_args(cfg, dev)
+    args = make_args(cfg, dev, peer_optimizer=opts.peer_optimizer)
     cap, B = cfg["cap"], cfg["B"]
 
     mem = ReplayMemory(args, cap, seed=shard_seed(17, rank))
@@ -471,6 +471,8 @@ def main():
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--cpu-updates", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--peer-optimizer", action="store_true",
+                    help="N>1: fused reduce-scatter + clip + Adam + all-gather over NVLink peer memory instead of NCCL all-reduce")
     ap.add_argument("--profile-steps", type=int, default=0, help="run this many steps inside cudaProfilerStart/Stop and exit")
     ap.add_argument("--profile-mode", default="graph", choices=["graph", "eager", "e2e"])
     opts = ap.parse_args()

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define RB_ABI_VERSION 1
+#define RB_ABI_VERSION 2
 
 #define RB_OK 0
 #define RB_ERR_INVAL (-22)       /* bad argument (EINVAL) */
@@ -58,8 +58,12 @@ extern "C" {
 #define RB_MAX_PEERS 8           /* ranks of one NVLink domain handled by rb_peer_clip_adam */
 #define RB_APPEND_BATCH 8        /* transitions per rb_append_batch launch */
 
-/* status word layout written by rb_tree_sample: status[0] = 1 if the batch now in the
- * output buffers passed the whole-batch validity test, 0 otherwise; status[1] = draws used. */
+/* status words written by rb_tree_sample (int32[4]): status[0] = 1 if the batch now in the output buffers passed the
+ * whole-batch validity test (memory.py:131), 0 otherwise; status[1] = draws used; status[2] = number of device-RNG
+ * batches so far that were still invalid after max_attempts draws (cumulative; the caller zero-initialises it once).
+ * A rejected batch has all its importance weights set to 0 (its loss gradient is exactly zero), and status[0] can be
+ * handed as the `gate` of rb_clip_adam / rb_tree_update so neither the parameters nor the priorities are touched --
+ * the device-side counterpart of the reference's redraw-until-valid loop (memory.py:128-132), without a host sync. */
 
 typedef void* rb_stream_t; /* cudaStream_t */
 
@@ -67,7 +71,8 @@ typedef void* rb_stream_t; /* cudaStream_t */
 enum {
   RB_K_TREE_UPDATE = 0, RB_K_TREE_FIND, RB_K_TREE_SAMPLE, RB_K_GATHER, RB_K_ITER_STATES, RB_K_APPEND, RB_K_C51,
   RB_K_NOISY_RESAMPLE, RB_K_NOISY_COMPOSE, RB_K_SQNORM, RB_K_CLIP_ADAM, RB_K_HEAD_FC1, RB_K_HEAD_FC2, RB_K_HEAD_LOGITS,
-  RB_K_HEAD_WGRAD2, RB_K_HEAD_DH, RB_K_HEAD_BWD1, RB_K_NOISE_FACTORS, RB_K_C51_DUELING, RB_K_BIAS_GRAD, RB_KERNEL_COUNT
+  RB_K_HEAD_WGRAD2, RB_K_HEAD_DH, RB_K_HEAD_BWD1, RB_K_NOISE_FACTORS, RB_K_C51_DUELING, RB_K_BIAS_GRAD, RB_K_Q_VALUES,
+  RB_KERNEL_COUNT
 };
 
 int rb_abi_version(void);
@@ -84,10 +89,11 @@ int rb_profile_collect(int kernel_id, double* total_ms, int* launches);
  * leaf[tree_idx[k]] = raw_priority[k]^omega (duplicates: last k wins), parents recomputed
  * level by level as fl32(left+right) up to the root, running_max = max(running_max, max_k leaf).
  * omega_is_applied != 0 means raw_priority already holds exponentiated values (SegmentTree.update).
- * status[0] is set to 1 if any tree_idx lies outside the leaf range (nothing is written for it). */
+ * status[0] is set to 1 if any tree_idx lies outside the leaf range (nothing is written for it).
+ * gate (optional device int32, may be NULL): when *gate == 0 the launch does nothing (rejected sample batch). */
 int rb_tree_update(float* tree, int64_t tree_start, int64_t size, const int64_t* tree_idx,
                    const float* raw_priority, float omega, int omega_is_applied, int B, float* running_max,
-                   int32_t* status, rb_stream_t stream);
+                   int32_t* status, const int32_t* gate, rb_stream_t stream);
 
 /* memory.py:79-82 SegmentTree.find (-> :64-76 _retrieve): float64 residual against float32 nodes,
  * strict '>' goes right, child indices clipped to the last element on the leaf level. */
@@ -134,7 +140,7 @@ int rb_append(float* tree, int64_t tree_start, int64_t size, uint8_t* frames, in
 /* k consecutive rb_append calls in ONE launch (actor side batching): HOST arrays of length k --
  * last_frames[j] points at the j-th newest frame (float32[84*84], DEVICE memory or PINNED HOST memory, read in place),
  * actions / rewards / terminals its fields.  Result is identical to k rb_append calls in order.  1 <= k <= RB_APPEND_BATCH.
- * [round-1 status: compiled, not yet exercised on hardware -- ReplayMemory(defer_appends=True) is off by default] */
+ * (ReplayMemory(defer_appends=True) uses it.) */
 int rb_append_batch(float* tree, int64_t tree_start, int64_t size, uint8_t* frames, int32_t* timestep, int32_t* action,
                     float* reward, uint8_t* nonterminal, int64_t* ring_state, float* running_max,
                     const float* const* last_frames, const int32_t* actions, const float* rewards, const int32_t* terminals,
@@ -225,6 +231,12 @@ int rb_head_logits(const float* z, int M, int actions, int atoms, float* q, rb_s
 int rb_head_backward(const rb_head_params* p, const rb_head_grads* g, const float* x, const float* h, const float* dz, int B,
                      float* dh_scratch, float* dx, int relu_mask_x, int parts, rb_stream_t stream);
 
+/* agent.py:53-55 Agent.act / :110-112 evaluate_q after the network body, for M states at once: from the head output
+ * z[M][atoms*(1+actions)] computes q[m][a] = sum_z support_z * softmax_z(zv + za[a] - mean_a za) (model.py:75-79) and its
+ * arg-max / max over actions.  q (float32[M][actions]), best_action (int64[M]), best_q (float32[M]) are each optional. */
+int rb_q_values(const float* z, int M, int actions, int atoms, const float* support, float* q, int64_t* best_action,
+                float* best_q, rb_stream_t stream);
+
 /* Bias gradient of a conv layer (the sum over batch and pixels torch computes in convolution_backward):
  * out[c] = sum_{b,p} grad_out[b][c][p], grad_out float32[B][C][HW] contiguous. */
 int rb_bias_grad(const float* grad_out, int B, int C, int HW, float* out, rb_stream_t stream);
@@ -248,22 +260,38 @@ int rb_noisy_compose(const float* mu, const float* sigma, const float* eps, int6
  * before everything else (1/world_size after a SUM all-reduce; 1.0 on one GPU).
  * partial_sums: scratch float64[rb_clip_adam_scratch_elems()], ZERO-INITIALISED once by the caller (its last element is a
  * self-resetting completion ticket).  norm_out (optional) receives the
- * pre-clip global L2 norm. */
+ * pre-clip global L2 norm.  gate (optional device int32, may be NULL): when *gate == 0 neither the parameters, the
+ * moments nor step_count change (rejected sample batch, see rb_tree_sample). */
 int rb_clip_adam_scratch_elems(void);
 int rb_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t P, float grad_scale,
                  float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_count,
-                 double* partial_sums, float* norm_out, rb_stream_t stream);
+                 double* partial_sums, float* norm_out, const int32_t* gate, rb_stream_t stream);
 
 /* Multi-GPU replacement of "all-reduce the flat gradient, then rb_clip_adam on every rank" (agent.py:97-98 under data
- * parallelism; no reference counterpart): reduce-scatter by peer loads + clip + Adam on the owned 1/world slice (moments
+ * parallelism; no reference counterpart): reduce-scatter by peer loads + clip + Adam on the owned 1/world parts (moments
  * sharded) + all-gather by peer stores, ordered by epoch flags in peer-visible memory.  HOST arrays of length `world`:
- * peer_grad[q] / peer_param[q] = rank q's flat gradient / parameter buffer (P floats, P % (4*world) == 0),
- * peer_flags[q] = rank q's uint64[3*world] flag block, peer_norms[q] = rank q's double[world] block (both zero-initialised
- * once), all mapped on this device.  gred: float32[P/world] scratch; exp_avg / exp_avg_sq: float32[P/world] (this rank's
- * shard); epoch: device uint64 (zero-initialised, advanced by the call); scratch: rb_peer_scratch_bytes() zeroed bytes.
- * grad_scale multiplies the reduced gradient (1/world for averaging).  Every rank must make the same call each step.
- * [round-1 status: compiled, not yet exercised on hardware] */
+ * peer_grad[q] / peer_param[q] = rank q's flat gradient / parameter buffer, peer_flags[q] = rank q's uint64[4*world] flag
+ * block, peer_norms[q] = rank q's double[world] block (both zero-initialised once), all mapped on this device.
+ * epoch: device uint64 (zero-initialised, advanced once per step by rb_peer_adam_gather); scratch: rb_peer_scratch_bytes()
+ * zeroed bytes.  Every rank must make the same calls each step.
+ *
+ * The flat buffer is exchanged as one or two SEGMENTS [seg_begin, seg_begin + seg_len) (seg_len % (4*world) == 0); rank r
+ * owns part r (seg_len / world elements) of each.  rb_peer_reduce reduces one segment (it may be enqueued on another
+ * stream as soon as that segment's gradients are final -- the learner sends the noisy-head segment while the conv backward
+ * still runs); gred_part receives this rank's reduced part, multiplied by grad_scale (1/world for averaging).
+ * rb_peer_adam_gather (after every segment's rb_peer_reduce, stream-ordered) publishes the partial norms, clips, runs Adam
+ * on the owned parts -- gred / exp_avg / exp_avg_sq hold the parts of segment 0, then segment 1, back to back --, stores the
+ * new parameters into every rank's buffer and returns when all ranks' parts have landed here.
+ * rb_peer_clip_adam = rb_peer_reduce over [0, P) + rb_peer_adam_gather with that single segment.
+ * Validated on 4 x B200 against NCCL all-reduce + rb_clip_adam (tools/peer_adam_check.py). */
 int rb_peer_scratch_bytes(void);
+int rb_peer_reduce(const float* const* peer_grad, uint64_t* const* peer_flags, int world, int rank, int seg, int64_t seg_begin,
+                   int64_t seg_len, float grad_scale, float* gred_part, const uint64_t* epoch, void* scratch,
+                   rb_stream_t stream);
+int rb_peer_adam_gather(float* const* peer_param, uint64_t* const* peer_flags, double* const* peer_norms, int world, int rank,
+                        int n_seg, const int64_t* seg_begin, const int64_t* seg_len, const float* gred, float* exp_avg,
+                        float* exp_avg_sq, float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_count,
+                        uint64_t* epoch, void* scratch, float* norm_out, rb_stream_t stream);
 int rb_peer_clip_adam(const float* const* peer_grad, float* const* peer_param, uint64_t* const* peer_flags,
                       double* const* peer_norms, int world, int rank, int64_t P, float* gred, float* exp_avg,
                       float* exp_avg_sq, float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps,

@@ -32,7 +32,7 @@ SIGNATURES = {
     "rb_last_error": (C.c_char_p, []),
     "rb_profile_enable": (C.c_int, [_i32]),
     "rb_profile_collect": (C.c_int, [_i32, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
-    "rb_tree_update": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _f32, _i32, _i32, _vp, _vp, _vp]),
+    "rb_tree_update": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _f32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "rb_tree_find": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _vp, _vp, _vp, _vp]),
     "rb_tree_sample": (C.c_int, [_vp, _i64, _i64, _vp, _i32, _i32, _vp, _i32, _u64, _vp, _i32, _f32, _vp, _i32,
                                  _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -56,10 +56,14 @@ SIGNATURES = {
                                            _vp, _vp, _vp, _vp, _vp]),
     "rb_noisy_compose": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "rb_peer_scratch_bytes": (C.c_int, []),
+    "rb_peer_reduce": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _f32, _vp, _vp, _vp, _vp]),
+    "rb_peer_adam_gather": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32,
+                                      _vp, _vp, _vp, _vp, _vp]),
     "rb_peer_clip_adam": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _f32,
                                     _vp, _vp, _vp, _vp, _vp]),
     "rb_clip_adam_scratch_elems": (C.c_int, []),
-    "rb_clip_adam": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
+    "rb_clip_adam": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
+    "rb_q_values": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
 }
 
 
@@ -83,7 +87,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.rb_abi_version() != 1:
+    if lib.rb_abi_version() != 2:
         raise RainbowB200Error("librainbow_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -112,7 +116,7 @@ def stream():
 
 KERNEL_IDS = ["tree_update", "tree_find", "tree_sample", "gather", "iter_states", "append", "c51", "noisy_resample",
               "noisy_compose", "sqnorm", "clip_adam", "head_fc1", "head_fc2", "head_logits", "head_wgrad2", "head_dh",
-              "head_bwd1", "noise_factors", "c51_dueling", "bias_grad"]  # order of the enum in include/rainbow_b200.h
+              "head_bwd1", "noise_factors", "c51_dueling", "bias_grad", "q_values"]  # order of the enum in include/rainbow_b200.h
 
 
 class KernelTimer:

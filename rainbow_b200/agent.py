@@ -17,6 +17,8 @@ Nothing in that chain synchronises with the host, so the whole update is capture
 (the reference issues ~600 ATen ops per update).
 """
 import os
+import warnings
+import weakref
 
 import numpy as np
 import torch
@@ -82,10 +84,10 @@ class FusedClipAdam:
             self.conv_end = off
         self.lr, self.eps, self.max_norm, self.betas = float(lr), float(eps), float(max_norm), betas
         self.peer = None
-        if peer:   # [round-1 status: untested on hardware] buffers in symmetric memory, optimiser fused with the exchange
+        if peer:   # buffers in symmetric memory, optimiser fused with the gradient exchange (csrc/rb_peer.cu)
             from .peer import PeerOptimizerState
-            self.peer = PeerOptimizerState(off, dev)
-            self.numel = off = self.peer.numel
+            # segment 0 = noisy head (final first, reduced while the conv backward runs), segment 1 = conv parameters
+            self.peer = PeerOptimizerState(off, dev, segments=[(self.conv_end, off), (0, self.conv_end)])
             self.flat_param, self.flat_grad = self.peer.flat_param, self.peer.flat_grad
             self.exp_avg, self.exp_avg_sq = self.peer.exp_avg, self.peer.exp_avg_sq
         else:
@@ -111,14 +113,17 @@ class FusedClipAdam:
         """Only the conv parameters accumulate through autograd on the fused path; the head kernels overwrite theirs."""
         self.flat_grad[:self.conv_end].zero_()
 
-    def step(self, grad_scale=1.0):
+    def step(self, grad_scale=1.0, gate=None):
+        """`gate`: optional device int32 (ReplayMemory.sample_gate()); when its first element is 0 the step is skipped on
+        the device (single-GPU only: data-parallel ranks must step in lock step, there a rejected batch simply contributes
+        a zero gradient through its zeroed importance weights)."""
         if self.peer is not None:   # reduce-scatter + clip + Adam + all-gather over peer memory (1/world folded in)
             self.peer.step(self.max_norm, self.lr, self.betas, self.eps)
             return
         _lib.check(self._lib.rb_clip_adam(
             _lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
             self.numel, float(grad_scale), self.max_norm, self.lr, self.betas[0], self.betas[1], self.eps,
-            _lib.ptr(self.step_count), _lib.ptr(self._partial), _lib.ptr(self.grad_norm), _lib.stream()))
+            _lib.ptr(self.step_count), _lib.ptr(self._partial), _lib.ptr(self.grad_norm), _lib.ptr(gate), _lib.stream()))
 
     def state_dict(self):
         return dict(step=int(self.step_count.item()), exp_avg=self.exp_avg.clone(), exp_avg_sq=self.exp_avg_sq.clone(),
@@ -135,7 +140,15 @@ class Agent:
         self.device = torch.device(args.device)
         if self.device.type != "cuda":
             raise _lib.RainbowB200Error(f"rainbow_b200.Agent needs a CUDA device, got '{self.device}' (no CPU fallback)")
+        # Precision policy (documented switch, default = the reference's arithmetic): the learner computes in true fp32.
+        # `args.tf32 = True` lets cuDNN / cuBLAS use TF32 tensor cores for the conv body (north star: "tensor cores only
+        # there"); the parity tests and bench.py run with the default.  torch keeps these flags per process, so the
+        # Agent sets them: what is measured is what ships.
+        self.tf32 = bool(getattr(args, "tf32", False))
+        torch.backends.cudnn.allow_tf32 = self.tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.tf32
         self.action_space = env.action_space()
+        self.history = int(getattr(args, "history_length", 4))
         self.atoms = args.atoms
         self.Vmin = args.V_min
         self.Vmax = args.V_max
@@ -179,27 +192,107 @@ class Agent:
 
         self.use_cuda_graph = bool(getattr(args, "cuda_graph", True))
         self.use_fused_head = bool(getattr(args, "fused_head", True))
+        self._step_gate = None
         self._streams = None
         self._graph = None
-        self._graph_key = None
+        self._graph_key = None    # (weakref to the memory the graph was captured for, batch size)
         self._ws = None
         self._learn_calls = 0
+        self._rejected_seen = 0
+        self._q_graphs = {}       # training-mode flag -> captured one-state act / evaluate_q graph
         self.last_loss = None  # per-sample losses of the most recent update (device tensor)
 
     # ---- acting / evaluation (agent.py:49-59,110-118) ---------------------------------------------
     def reset_noise(self):
         self.online_net.reset_noise()
 
-    def act(self, state):
+    def q_select(self, states, q_out=None):
+        """Greedy action and its value for a batch of states [N, history, 84, 84] (device): conv body (cuDNN), fused
+        noisy dueling head, then rb_q_values -- softmax over atoms, expectation over the support (agent.py:55) and the
+        arg-max / max over actions in one launch.  Returns device tensors (actions int64[N], values float32[N]); nothing
+        synchronises.  Falls back to plain torch ops for head shapes the fused kernels do not cover."""
+        on = self.online_net
+        N = states.shape[0]
         with torch.no_grad():
-            return (self.online_net(state.unsqueeze(0)) * self.support).sum(2).argmax(1).item()
+            if on.fused_ok(N):
+                x = on.features_nograd(states).contiguous()
+                z, _, _ = on.head().forward(x)
+                best_a = torch.empty(N, dtype=torch.int64, device=self.device)
+                best_q = torch.empty(N, dtype=torch.float32, device=self.device)
+                _lib.check(_lib.load().rb_q_values(_lib.ptr(z), N, self.action_space, self.atoms, _lib.ptr(self.support),
+                                                   _lib.ptr(q_out), _lib.ptr(best_a), _lib.ptr(best_q), _lib.stream()))
+                return best_a, best_q
+            q = (on(states) * self.support).sum(2)
+            if q_out is not None:
+                q_out.copy_(q)
+            best_q, best_a = q.max(1)
+            return best_a, best_q
+
+    def _one_state(self, state):
+        """One state through a captured CUDA graph (conv x3, fused head x2, rb_q_values): returns pinned host tensors
+        (action int64[1], value float32[1]) after ONE device-to-host copy and one event wait -- the per-env-step cost of
+        main.py:139,153 / test.py:26 instead of ~40 eager launches and a blocking .item()."""
+        on = self.online_net
+        key = bool(on.training)
+        g = self._q_graphs.get(key)
+        if g is None:
+            g = dict(inp=torch.zeros((1, self.history, 84, 84), dtype=torch.float32, device=self.device),
+                     host=torch.zeros(2, dtype=torch.float64).pin_memory(), dev=torch.zeros(2, dtype=torch.float64, device=self.device),
+                     done=torch.cuda.Event(), graph=None, warm=0)
+            self._q_graphs[key] = g
+
+        def run():
+            a, q = self.q_select(g["inp"])
+            g["dev"][0:1].copy_(a)      # both results in one small buffer -> one D2H copy
+            g["dev"][1:2].copy_(q)
+
+        g["inp"].copy_(state.reshape(g["inp"].shape), non_blocking=True)
+        if not self.use_cuda_graph:
+            run()
+        elif g["graph"] is None and g["warm"] < 2:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                run()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g["warm"] += 1
+        else:
+            if g["graph"] is None:
+                torch.cuda.synchronize(self.device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    run()
+                g["graph"] = graph
+            g["graph"].replay()
+        g["host"].copy_(g["dev"], non_blocking=True)
+        g["done"].record(torch.cuda.current_stream(self.device))
+        g["done"].synchronize()
+        return g["host"]
+
+    def act(self, state):
+        """agent.py:53-55."""
+        return int(self._one_state(state)[0])
 
     def act_e_greedy(self, state, epsilon=0.001):
         return np.random.randint(0, self.action_space) if np.random.random() < epsilon else self.act(state)
 
     def evaluate_q(self, state):
-        with torch.no_grad():
-            return (self.online_net(state.unsqueeze(0)) * self.support).sum(2).max(1)[0].item()
+        """agent.py:110-112 (one state -> float).  For many states use evaluate_q_batch / evaluate_q_memory."""
+        return float(self._one_state(state)[1])
+
+    def evaluate_q_batch(self, states):
+        """max_a Q(s, a) for states [N, history, 84, 84]: device float32[N], no synchronisation."""
+        return self.q_select(states)[1]
+
+    def evaluate_q_memory(self, val_mem, chunk=64):
+        """test.py:37-41 `for state in val_mem: T_Qs.append(dqn.evaluate_q(state))` as batched passes over the validation
+        memory's iterator states (rb_iter_states -> conv -> fused head -> rb_q_values) and a single read-back.
+        Returns the list of floats that loop would have produced."""
+        outs = []
+        for first in range(0, val_mem.capacity, chunk):
+            count = min(chunk, val_mem.capacity - first)
+            outs.append(self.q_select(val_mem.iter_states(first, count))[1])
+        return torch.cat(outs).cpu().tolist() if outs else []
 
     def train(self):
         self.online_net.train()
@@ -294,13 +387,17 @@ class Agent:
                 main.wait_event(w2_done)
                 head_ready = None
                 if self.sync.enabled:
-                    # 99 % of the gradient bytes (the noisy head) are final here: start their all-reduce on a side
-                    # stream so it overlaps the conv backward; the conv slice (a few hundred KB) follows afterwards
+                    # 99 % of the gradient bytes (the noisy head) are final here: start their exchange on a side
+                    # stream so it overlaps the conv backward; the conv slice (a few hundred KB) follows afterwards.
+                    # Peer optimiser: reduce-scatter by NVLink peer loads (rb_peer_reduce); else NCCL all-reduce.
                     head_ready = torch.cuda.Event()
                     head_ready.record(main)
                     with torch.cuda.stream(s_tg):
                         s_tg.wait_event(head_ready)
-                        self.sync.all_reduce_(self.optimiser.flat_grad[self.optimiser.conv_end:])
+                        if self.optimiser.peer is not None:
+                            self.optimiser.peer.reduce_segment(0)
+                        else:
+                            self.sync.all_reduce_(self.optimiser.flat_grad[self.optimiser.conv_end:])
                         head_reduced = torch.cuda.Event()
                         head_reduced.record(s_tg)
                 grads_done = on.conv_backward_into_grads(acts, dx.view_as(acts[-1]), s_ns)
@@ -314,14 +411,16 @@ class Agent:
         if not manual:
             x_s.backward(dx)
             self.sync.all_reduce_(self.optimiser.flat_grad)
-        self.optimiser.step(grad_scale=1.0 / self.sync.world_size)
+        self.optimiser.step(grad_scale=1.0 / self.sync.world_size, gate=self._step_gate)
         if wb_done is not None:
             main.wait_event(wb_done)
         return loss
 
-    def _update_from_batch(self, batch, target_noise=None, after_loss=None):
+    def _update_from_batch(self, batch, target_noise=None, after_loss=None, gate=None):
         """agent.py:66-98 on an already sampled batch; returns per-sample losses (device).  `after_loss(loss)`, if
-        given, is called as soon as the losses exist (the fused path runs it on a side stream)."""
+        given, is called as soon as the losses exist (the fused path runs it on a side stream).  `gate`: the sample's
+        status words; a rejected batch leaves the parameters untouched (world 1)."""
+        self._step_gate = gate if self.sync.world_size == 1 else None
         if self._fused_path(batch[1].shape[0]):
             return self._update_fused(batch, target_noise, after_loss)
         idxs, states, actions, returns, next_states, nonterminals, weights = batch
@@ -338,7 +437,7 @@ class Agent:
         self.optimiser.zero_grad()
         q_s.backward(grad)
         self.sync.all_reduce_(self.optimiser.flat_grad)
-        self.optimiser.step(grad_scale=1.0 / self.sync.world_size)
+        self.optimiser.step(grad_scale=1.0 / self.sync.world_size, gate=self._step_gate)
         if after_loss is not None:
             after_loss(loss)
         return loss
@@ -346,7 +445,9 @@ class Agent:
     def _learn_eager(self, mem):
         batch = mem.sample(self.batch_size)
         if isinstance(mem, ReplayMemory):
-            return self._update_from_batch(batch, after_loss=lambda loss: mem.update_priorities(batch[0], loss))
+            gate = mem.sample_gate()
+            return self._update_from_batch(batch, after_loss=lambda loss: mem.update_priorities(batch[0], loss, gate=gate),
+                                           gate=gate)
         loss = self._update_from_batch(batch)
         mem.update_priorities(batch[0], loss.detach().cpu().numpy())  # a foreign (reference-style, host) memory: agent.py:100
         return loss
@@ -361,7 +462,8 @@ class Agent:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             batch = mem.sample_into(ws)
-            loss = self._update_from_batch(batch, after_loss=lambda l: mem.update_priorities(batch[0], l))
+            loss = self._update_from_batch(batch, after_loss=lambda l: mem.update_priorities(batch[0], l, gate=ws.status),
+                                           gate=ws.status)
         self._graph, self._ws, self.last_loss = graph, ws, loss
 
     GRAPH_WARMUP = 2  # eager updates before capture (cuDNN/cuBLAS plan selection, autograd buffers)
@@ -373,9 +475,10 @@ class Agent:
         # the captured graph bakes in: this memory's buffers, the batch size and training-mode (noisy) weights
         graphable = (self.use_cuda_graph and isinstance(mem, ReplayMemory) and mem.rng == "philox" and
                      self.online_net.training)
-        key = (mem, self.batch_size)   # holds a reference: a recycled id() can never alias a dead memory's graph
-        if graphable and (self._graph_key is None or self._graph_key[0] is not mem or self._graph_key[1] != self.batch_size):
-            self._graph, self._graph_key, self._warm = None, key, 0
+        # weak reference: the agent must not keep a dropped 7 GB replay alive; a dead or different referent, or another
+        # batch size, invalidates the captured graph (a recycled id() can never alias a dead memory's graph)
+        if graphable and (self._graph_key is None or self._graph_key[0]() is not mem or self._graph_key[1] != self.batch_size):
+            self._graph, self._ws, self._graph_key, self._warm = None, None, (weakref.ref(mem), self.batch_size), 0
         if not graphable:
             self.last_loss = self._learn_eager(mem)
         elif self._graph is None and self._warm < self.GRAPH_WARMUP:
@@ -393,4 +496,10 @@ class Agent:
             self._graph.replay()
         self._learn_calls += 1
         if self._learn_calls % 4096 == 0 and isinstance(mem, ReplayMemory):
-            mem.check_last_sample()
+            # diagnostics only (the device already skipped such updates): how many batches stayed invalid after
+            # max_attempts redraws -- a ring that is too empty around the write head, or zero-priority leaves
+            rejected = mem.rejected_batches()
+            if rejected > self._rejected_seen:
+                warnings.warn(f"rainbow_b200: {rejected - self._rejected_seen} sampled batches were rejected "
+                              f"{mem.max_attempts} times in a row and skipped (no update, no priority write-back)")
+            self._rejected_seen = rejected

@@ -80,7 +80,8 @@ constexpr int UPD_THREADS = 1024;
 __global__ void __launch_bounds__(UPD_THREADS, 1)
 k_tree_update(float* tree, int64_t tree_start, int64_t size, const int64_t* __restrict__ tree_idx,
               const float* __restrict__ raw, float omega, int omega_is_applied, int B, float* running_max,
-              int32_t* status) {
+              int32_t* status, const int32_t* __restrict__ gate) {
+  if (gate && *gate == 0) return;   // the batch these priorities belong to was rejected by rb_tree_sample: leave the tree alone
   __shared__ int64_t s_idx[UPD_THREADS];
   __shared__ float s_red[32];
   const int tid = threadIdx.x;
@@ -145,7 +146,8 @@ constexpr int UPD_MAX_LEVELS = 30;
 __global__ void __launch_bounds__(32, 1)
 k_tree_update_warp(float* tree, int64_t tree_start, int64_t size, const int64_t* __restrict__ tree_idx,
                    const float* __restrict__ raw, float omega, int omega_is_applied, int B, float* running_max,
-                   int32_t* status) {
+                   int32_t* status, const int32_t* __restrict__ gate) {
+  if (gate && *gate == 0) return;   // rejected batch (see k_tree_update)
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x;
   const int64_t len = tree_start + size;
@@ -393,10 +395,15 @@ k_tree_sample(const float* __restrict__ tree, int64_t tree_start, int64_t size, 
   if (lane == 0) s_red[warp] = wmax;
   __syncthreads();
   wmax = warp_max(s_red[lane]);
-  for (int k = tid; k < B; k += blockDim.x) weights[k] = __fdiv_rn(k == tid ? w_first : weights[k], wmax);
+  // A batch that is still invalid after the last allowed redraw (the reference would keep redrawing, memory.py:128-132)
+  // must not train anything: its weights are zeroed -- so the loss gradient is exactly zero -- and status[0] = 0 gates
+  // the optimiser step and the priority write-back (rb_clip_adam / rb_tree_update `gate`).
+  for (int k = tid; k < B; k += blockDim.x)
+    weights[k] = ok_batch ? __fdiv_rn(k == tid ? w_first : weights[k], wmax) : 0.0f;
   if (tid == 0) {
     status[0] = ok_batch ? 1 : 0;
     status[1] = attempt;
+    if (!ok_batch && u01 == nullptr) status[2] = status[2] + 1;   // batches rejected for good so far (host diagnostics)
     if (u01 == nullptr) *rng_counter = ctr0 + (unsigned long long)attempt;
   }
 }
@@ -977,6 +984,69 @@ k_c51_dueling(const float* __restrict__ z_on, const float* __restrict__ z_tg, co
 }
 
 // ================================================================================================
+// Q-values for acting / evaluation (agent.py:53-55 act, :110-112 evaluate_q): one warp per state.
+// From the head output z = (z_value | z_advantage): q[a][z] = zv + za[a] - mean_a za (model.py:75), softmax over
+// atoms (model.py:79), expected value sum_z support_z p_z (agent.py:55), then the arg-max / max over actions --
+// everything after the network body in ONE launch, results stay on the device (no .item() per state).
+// ================================================================================================
+__global__ void __launch_bounds__(128)
+k_q_select(const float* __restrict__ z, int M, int A, int Z, const float* __restrict__ support, float* __restrict__ q_out,
+           int64_t* __restrict__ best_action, float* __restrict__ best_q) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 4 + warp;
+  if (m >= M) return;
+  const float* zr = z + (size_t)m * (Z + A * Z);
+  constexpr int R = RB_MAX_ATOMS / 32;
+  float sup[R], zv[R], mean[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int c = lane + 32 * r;
+    sup[r] = zv[r] = mean[r] = 0.0f;
+    if (c < Z) {
+      sup[r] = __ldg(support + c);
+      zv[r] = __ldg(zr + c);
+      float acc = 0.0f;
+      for (int a = 0; a < A; ++a) acc += __ldg(zr + Z + a * Z + c);
+      mean[r] = acc / (float)A;
+    }
+  }
+  int best = 0;
+  float best_ev = -CUDART_INF_F;
+  for (int a = 0; a < A; ++a) {
+    float x[R], mx = -CUDART_INF_F;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int c = lane + 32 * r;
+      x[r] = (c < Z) ? zv[r] + __ldg(zr + Z + a * Z + c) - mean[r] : -CUDART_INF_F;
+      mx = fmaxf(mx, x[r]);
+    }
+    mx = warp_max(mx);
+    float se = 0.0f, sn = 0.0f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float ee = (lane + 32 * r < Z) ? expf(x[r] - mx) : 0.0f;
+      se = __fadd_rn(se, ee);
+      sn = __fadd_rn(sn, __fmul_rn(sup[r], ee));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      se = __fadd_rn(se, __shfl_xor_sync(0xffffffffu, se, o));
+      sn = __fadd_rn(sn, __shfl_xor_sync(0xffffffffu, sn, o));
+    }
+    const float ev = __fdiv_rn(sn, se);
+    if (q_out && lane == 0) q_out[(size_t)m * A + a] = ev;
+    if (ev > best_ev) {   // first maximum wins, like torch.argmax / max
+      best_ev = ev;
+      best = a;
+    }
+  }
+  if (lane == 0) {
+    if (best_action) best_action[m] = best;
+    if (best_q) best_q[m] = best_ev;
+  }
+}
+
+// ================================================================================================
 // K6  noisy_resample : factorised Gaussian noise for every NoisyLinear of one net, one launch.
 // ================================================================================================
 struct NoisyPlan {
@@ -1138,7 +1208,8 @@ __global__ void __launch_bounds__(ADAM_THREADS)
 k_clip_adam(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ exp_avg,
             float* __restrict__ exp_avg_sq, int64_t P, float grad_scale, float max_norm, float lr, float b1, float b2,
             float eps, int64_t* __restrict__ step_count, const double* __restrict__ partial, int n_partial,
-            float* __restrict__ norm_out, unsigned int* __restrict__ done_ticket) {
+            float* __restrict__ norm_out, unsigned int* __restrict__ done_ticket, const int32_t* __restrict__ gate) {
+  const bool skip = gate && *gate == 0;   // rejected sample batch: no parameter update, no step (see k_tree_sample)
   __shared__ double s_red[ADAM_THREADS / 32];
   __shared__ float s_coef;
   // every CTA re-reduces the (few hundred) partial sums in the same order: deterministic, no atomics
@@ -1167,7 +1238,8 @@ k_clip_adam(float* __restrict__ param, const float* __restrict__ grad, float* __
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool vec = (P & 3) == 0 && (((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0;
-  if (vec) {
+  if (skip) {
+  } else if (vec) {
     for (; i < (P >> 2); i += stride) {
       float4 p = reinterpret_cast<float4*>(param)[i], g = __ldg(reinterpret_cast<const float4*>(grad) + i),
              m = reinterpret_cast<float4*>(exp_avg)[i], v = reinterpret_cast<float4*>(exp_avg_sq)[i];
@@ -1196,7 +1268,7 @@ k_clip_adam(float* __restrict__ param, const float* __restrict__ grad, float* __
     const unsigned int t = atomicAdd(done_ticket, 1u);
     if (t == gridDim.x - 1) {
       *done_ticket = 0u;
-      *step_count = step;
+      if (!skip) *step_count = step;
     }
   }
 }
@@ -1242,17 +1314,18 @@ int rb_profile_collect(int kernel_id, double* total_ms, int* launches) {
 const char* rb_last_error(void) { return rbi::g_err; }
 
 int rb_tree_update(float* tree, int64_t tree_start, int64_t size, const int64_t* tree_idx, const float* raw_priority,
-                   float omega, int omega_is_applied, int B, float* running_max, int32_t* status, rb_stream_t stream) {
+                   float omega, int omega_is_applied, int B, float* running_max, int32_t* status, const int32_t* gate,
+                   rb_stream_t stream) {
   if (!tree || !tree_idx || !raw_priority || !running_max) return fail(RB_ERR_INVAL, "rb_tree_update: null pointer");
   if (B <= 0 || size <= 0 || (size & 1)) return fail(RB_ERR_INVAL, "rb_tree_update: B > 0 and an even size are required");
   if (tree_start + size > ((int64_t)1 << 31)) return fail(RB_ERR_RANGE, "rb_tree_update: tree larger than 2^31 nodes");
   { ProfScope prof_(RB_K_TREE_UPDATE, (cudaStream_t)stream);
     if (B <= 32 && tree_depth(tree_start) <= 30)
       k_tree_update_warp<<<1, 32, 0, (cudaStream_t)stream>>>(tree, tree_start, size, tree_idx, raw_priority, omega,
-                                                            omega_is_applied, B, running_max, status);
+                                                            omega_is_applied, B, running_max, status, gate);
     else
       k_tree_update<<<1, UPD_THREADS, 0, (cudaStream_t)stream>>>(tree, tree_start, size, tree_idx, raw_priority, omega,
-                                                               omega_is_applied, B, running_max, status); }
+                                                               omega_is_applied, B, running_max, status, gate); }
   return check_launch("rb_tree_update");
 }
 
@@ -1473,6 +1546,17 @@ int rb_c51_dueling_loss_grad(const float* z_online, const float* z_target, int a
   return check_launch("rb_c51_dueling_loss_grad");
 }
 
+int rb_q_values(const float* z, int M, int actions, int atoms, const float* support, float* q, int64_t* best_action,
+                float* best_q, rb_stream_t stream) {
+  if (!z || !support) return fail(RB_ERR_INVAL, "rb_q_values: null pointer");
+  if (!q && !best_action && !best_q) return fail(RB_ERR_INVAL, "rb_q_values: no output requested");
+  if (M <= 0 || actions <= 0 || atoms <= 1) return fail(RB_ERR_INVAL, "rb_q_values: M, actions > 0 and atoms > 1 are required");
+  if (atoms > RB_MAX_ATOMS) return fail(RB_ERR_RANGE, "rb_q_values: atoms exceeds RB_MAX_ATOMS");
+  { ProfScope prof_(RB_K_Q_VALUES, (cudaStream_t)stream);
+    k_q_select<<<(M + 3) / 4, 128, 0, (cudaStream_t)stream>>>(z, M, actions, atoms, support, q, best_action, best_q); }
+  return check_launch("rb_q_values");
+}
+
 int rb_noisy_compose(const float* mu, const float* sigma, const float* eps, int64_t count, float* out, rb_stream_t stream) {
   if (!mu || !sigma || !eps || !out) return fail(RB_ERR_INVAL, "rb_noisy_compose: null pointer");
   if (count <= 0) return fail(RB_ERR_INVAL, "rb_noisy_compose: count must be positive");
@@ -1488,7 +1572,7 @@ int rb_clip_adam_scratch_elems(void) { return ADAM_MAX_CTAS + 1; }  // partial s
 
 int rb_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t P, float grad_scale,
                  float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_count, double* partial_sums,
-                 float* norm_out, rb_stream_t stream) {
+                 float* norm_out, const int32_t* gate, rb_stream_t stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || !step_count || !partial_sums)
     return fail(RB_ERR_INVAL, "rb_clip_adam: null pointer");
   if (P <= 0) return fail(RB_ERR_INVAL, "rb_clip_adam: P must be positive");
@@ -1500,7 +1584,7 @@ int rb_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg
   { ProfScope prof_(RB_K_CLIP_ADAM, (cudaStream_t)stream);
     k_clip_adam<<<ctas, ADAM_THREADS, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, P, grad_scale, max_norm, lr,
                                                                beta1, beta2, eps, step_count, partial_sums, ctas, norm_out,
-                                                               reinterpret_cast<unsigned int*>(partial_sums + ADAM_MAX_CTAS)); }
+                                                               reinterpret_cast<unsigned int*>(partial_sums + ADAM_MAX_CTAS), gate); }
   return check_launch("rb_clip_adam");
 }
 

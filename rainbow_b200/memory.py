@@ -74,6 +74,26 @@ class SegmentTree:
         self._status = torch.zeros(4, dtype=torch.int32, device=self.device)
         self._lib = _lib.load()
 
+    # ---- pickling: the reference pickles the whole object graph (main.py:85-100) ------------------------------
+    def __getstate__(self):
+        """The reference's own field layout (memory.py:13-20): index, size, full, tree_start, sum_tree, data, max."""
+        return dict(index=self.index, size=self.size, full=self.full, tree_start=self.tree_start, sum_tree=self.sum_tree,
+                    data=self.data, max=self.max)
+
+    def __setstate__(self, state):
+        """Accepts the reference's SegmentTree.__dict__ (a file written by the reference, loaded with dropin/ shadowing
+        the `memory` module).  The device arrays are created by _materialise() once the owning ReplayMemory knows the device."""
+        if not all(k in state for k in ("index", "size", "full", "sum_tree", "data", "max")):
+            raise _lib.RainbowB200Error("unknown SegmentTree pickle layout")
+        self._pending = dict(state)
+        self.size, self.index, self.full = int(state["size"]), int(state["index"]), bool(state["full"])
+        self.tree_start = 2 ** (self.size - 1).bit_length() - 1
+
+    def _materialise(self, device, t_episode=0):
+        fields = self.__dict__.pop("_pending")
+        SegmentTree.__init__(self, fields["size"], device)
+        self.load_arrays(**reference_fields_to_ring(fields, t=t_episode))
+
     # ---- reference-style accessors -------------------------------------------------------------
     @property
     def max(self):
@@ -102,9 +122,10 @@ class SegmentTree:
             return x.to(device=self.device, dtype=dtype).contiguous()
         return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(self.device, non_blocking=True)
 
-    def update(self, indices, values, omega=None):
+    def update(self, indices, values, omega=None, gate=None):
         """memory.py:44-48.  `values` are tree values; with `omega` given they are raw priorities and the
-        kernel applies ^omega (memory.py:158)."""
+        kernel applies ^omega (memory.py:158).  `gate`: optional device int32 tensor; the launch is a no-op when its
+        first element is 0 (the status word of a rejected sample batch)."""
         idx = self._as_dev(indices, torch.int64).reshape(-1)
         val = self._as_dev(values, torch.float32).reshape(-1)
         if idx.numel() != val.numel():
@@ -112,7 +133,7 @@ class SegmentTree:
         _lib.check(self._lib.rb_tree_update(
             _lib.ptr(self.tree), self.tree_start, self.size, _lib.ptr(idx), _lib.ptr(val),
             0.0 if omega is None else float(omega), 1 if omega is None else 0, idx.numel(),
-            _lib.ptr(self.running_max), _lib.ptr(self._status), _lib.stream()))
+            _lib.ptr(self.running_max), _lib.ptr(self._status), _lib.ptr(gate), _lib.stream()))
 
     def find(self, values):
         """memory.py:79-82: float64 values -> (leaf values, data indices, tree indices), as device tensors."""
@@ -126,11 +147,13 @@ class SegmentTree:
         return probs, didx, tidx
 
     def append_frame(self, last_frame, action, reward, terminal):
-        """memory.py:56-61 with the record fields passed separately; the leaf gets the running max."""
+        """memory.py:56-61 with the record fields passed separately; the leaf gets the running max.
+        `last_frame`: float32 [84*84] in device memory or PINNED host memory (read in place by the kernel)."""
+        fptr = last_frame.data_ptr() if (not last_frame.is_cuda and last_frame.is_pinned()) else _lib.ptr(last_frame)
         _lib.check(self._lib.rb_append(
             _lib.ptr(self.tree), self.tree_start, self.size, _lib.ptr(self.frames), _lib.ptr(self.timestep),
             _lib.ptr(self.action), _lib.ptr(self.reward), _lib.ptr(self.nonterminal), _lib.ptr(self.ring_state),
-            _lib.ptr(self.running_max), _lib.ptr(last_frame), int(action), float(reward), 1 if terminal else 0,
+            _lib.ptr(self.running_max), fptr, int(action), float(reward), 1 if terminal else 0,
             _lib.stream()))
         self.index = (self.index + 1) % self.size
         self.full = self.full or self.index == 0
@@ -184,7 +207,7 @@ class _SampleWorkspace:
         self.actions = torch.empty(B, dtype=i64, device=device)
         self.returns = torch.empty(B, dtype=f32, device=device)
         self.nonterminals = torch.empty((B, 1), dtype=f32, device=device)
-        self.status = torch.zeros(2, dtype=torch.int32, device=device)
+        self.status = torch.zeros(4, dtype=torch.int32, device=device)   # ok flag, draws used, rejected batches so far, -
 
     def as_tuple(self):
         return (self.tree_idx, self.states, self.actions, self.returns, self.next_states, self.nonterminals,
@@ -226,12 +249,17 @@ class ReplayMemory:
         self.n_step_scaling = torch.tensor([self.discount ** i for i in range(self.n)], dtype=torch.float32,
                                            device=self.device)
         self.transitions = SegmentTree(self.capacity, self.device)
-        self.seed = int(torch.initial_seed() if seed is None else seed) & (2 ** 64 - 1)
+        if seed is None:   # data-parallel ranks launched with one torch seed must not draw the same stratified uniforms
+            from .dist import GradSync, shard_seed
+            rank = GradSync().rank
+            seed = torch.initial_seed() if rank == 0 else shard_seed(torch.initial_seed(), rank)
+        self.seed = int(seed) & (2 ** 64 - 1)
         self._rng_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
         self._beta_dev = torch.full((1,), float(self.priority_weight), dtype=torch.float32, device=self.device)
         self._beta_pushed = float(self.priority_weight)
         self._lib = _lib.load()
         self._last = None
+        self._stage = None
 
     def push_beta(self):
         """Mirror the host attribute `priority_weight` (main.py:161 rewrites it every step) into the device
@@ -242,15 +270,51 @@ class ReplayMemory:
             self._beta_pushed = b
 
     # ---- append --------------------------------------------------------------------------------
+    STAGE_SLOTS = 16   # owned pinned staging frames for host-resident states (2 x APPEND_BATCH)
+
+    def _stage_host_frame(self, last):
+        """Copy a HOST frame into an owned pinned slot and return the slot (float32 [84*84], 16-byte aligned).
+
+        The reference copies the frame synchronously (memory.py:106); an asynchronous H2D copy straight from the caller's
+        buffer would race with an env that rewrites its (pinned) frame buffer in place.  The slot is reused only after the
+        kernel that consumed it has finished (event per slot), so the caller may do whatever it likes with `state` as
+        soon as append() returns."""
+        if self._stage is None:
+            self._stage = torch.empty((self.STAGE_SLOTS, FRAME), dtype=torch.float32).pin_memory()
+            self._stage_evt = [None] * self.STAGE_SLOTS
+            self._stage_next = 0
+        k = self._stage_next
+        self._stage_next = (k + 1) % self.STAGE_SLOTS
+        if self._stage_evt[k] is not None:
+            self._stage_evt[k].synchronize()
+            self._stage_evt[k] = None
+        slot = self._stage[k]
+        slot.view(84, 84).copy_(last)      # host memcpy (+ dtype conversion / de-striding if needed)
+        return k, slot
+
+    def _release_stage_slots(self, slots):
+        if slots:
+            evt = torch.cuda.Event()
+            evt.record(torch.cuda.current_stream(self.device))
+            for k in slots:
+                self._stage_evt[k] = evt
+
     def append(self, state, action, reward, terminal):
         """memory.py:105-108.  `state` is the float32 [history,84,84] frame stack in [0,1]; only the newest
-        frame is stored (quantised to uint8 on the device)."""
+        frame is stored (quantised to uint8 on the device).  Host frames are staged through owned pinned memory and read
+        by the kernel in place (no separate H2D copy launch); device frames are read in place."""
         last = state[-1]
-        if self.defer_appends and (last.is_cuda or last.is_pinned()):
+        slot_id = None
+        if not last.is_cuda:
+            slot_id, last = self._stage_host_frame(last)
+        else:
             last = last.to(torch.float32).contiguous()
             if last.data_ptr() % 16:
                 last = last.clone()
-            self._queue.append((last, int(action), float(reward), bool(terminal)))
+        if self.defer_appends:
+            # queued by reference: a DEVICE frame must not be modified by the caller before the flush (main.py's env
+            # builds a fresh state tensor every step); host frames are already copied into the staging ring
+            self._queue.append((last, int(action), float(reward), bool(terminal), slot_id))
             tr = self.transitions
             tr.index = (tr.index + 1) % tr.size       # host mirrors advance now, the device copy at the flush
             tr.full = tr.full or tr.index == 0
@@ -258,14 +322,9 @@ class ReplayMemory:
             if len(self._queue) >= self.APPEND_BATCH:
                 self.flush_appends()
             return
-        if self._queue:   # a frame that cannot be queued (pageable host memory) must not overtake queued ones
-            self.flush_appends()
-        if not last.is_cuda:
-            last = last.to(self.device, non_blocking=True)
-        last = last.to(torch.float32).contiguous()
-        if last.data_ptr() % 16:
-            last = last.clone()
         self.transitions.append_frame(last, action, reward, terminal)
+        if slot_id is not None:
+            self._release_stage_slots([slot_id])
         self.t = 0 if terminal else self.t + 1
 
     def flush_appends(self):
@@ -276,15 +335,16 @@ class ReplayMemory:
         q, self._queue = self._queue, []
         k = len(q)
         tr = self.transitions
-        frames = (C.c_void_p * k)(*[f.data_ptr() for f, _, _, _ in q])   # device or pinned-host pointers (UVA)
-        acts = (C.c_int32 * k)(*[a for _, a, _, _ in q])
-        rews = (C.c_float * k)(*[r for _, _, r, _ in q])
-        terms = (C.c_int32 * k)(*[1 if t else 0 for _, _, _, t in q])
+        frames = (C.c_void_p * k)(*[e[0].data_ptr() for e in q])   # device or pinned-host pointers (UVA)
+        acts = (C.c_int32 * k)(*[e[1] for e in q])
+        rews = (C.c_float * k)(*[e[2] for e in q])
+        terms = (C.c_int32 * k)(*[1 if e[3] else 0 for e in q])
         _lib.check(self._lib.rb_append_batch(
             _lib.ptr(tr.tree), tr.tree_start, tr.size, _lib.ptr(tr.frames), _lib.ptr(tr.timestep), _lib.ptr(tr.action),
             _lib.ptr(tr.reward), _lib.ptr(tr.nonterminal), _lib.ptr(tr.ring_state), _lib.ptr(tr.running_max), frames, acts,
             rews, terms, k, _lib.stream()))
-        self._flushed_refs = q   # keep the frames alive until the next flush (the launch is asynchronous)
+        self._release_stage_slots([e[4] for e in q if e[4] is not None])
+        self._flushed_refs = q   # keep device frames alive until the next flush (the launch is asynchronous)
 
     # ---- sample --------------------------------------------------------------------------------
     def _launch_sample(self, ws, u01=None, attempts=0):
@@ -335,19 +395,33 @@ class ReplayMemory:
             self.check_last_sample()
         return out
 
+    def sample_gate(self):
+        """Device int32 status words of the most recent sample (None in numpy-rng mode, where the host loop only ever
+        returns valid batches): element 0 is 0 when that batch was rejected `max_attempts` times.  The kernel has then
+        zeroed the batch's importance weights, and handing this tensor as `gate` to update_priorities() / the optimiser
+        makes the whole update a no-op -- the device-side stand-in for the reference's unbounded redraw loop
+        (memory.py:128-132)."""
+        return None if (self._last is None or self.rng == "numpy") else self._last.status
+
+    def rejected_batches(self):
+        """Synchronises.  Number of device-RNG batches (since this workspace was created) that stayed invalid after
+        `max_attempts` redraws and were therefore skipped."""
+        return 0 if self._last is None else int(self._last.status[2].item())
+
     def check_last_sample(self):
-        """Synchronises; raises if the most recent device-RNG sample exhausted max_attempts redraws."""
+        """Synchronises; raises if the most recent device-RNG sample exhausted max_attempts redraws (strict mode)."""
         if self._last is not None and int(self._last.status[0].item()) != 1:
             raise _lib.RainbowB200Error(
                 f"replay sampling rejected {self.max_attempts} consecutive batches (buffer too empty around the "
-                "write head, or zero-priority leaves): the batch in flight is not valid")
+                "write head, or zero-priority leaves): that batch was skipped (zero weights, no update)")
 
     # ---- priorities ----------------------------------------------------------------------------
-    def update_priorities(self, idxs, priorities):
-        """memory.py:157-159: raw per-sample losses -> ^omega -> leaves -> propagate to the root."""
+    def update_priorities(self, idxs, priorities, gate=None):
+        """memory.py:157-159: raw per-sample losses -> ^omega -> leaves -> propagate to the root.
+        `gate` (optional, see sample_gate()): skip the write-back of a rejected batch on the device."""
         if self._queue and not torch.cuda.is_current_stream_capturing():
             self.flush_appends()
-        self.transitions.update(idxs, priorities, omega=self.priority_exponent)
+        self.transitions.update(idxs, priorities, omega=self.priority_exponent, gate=gate)
 
     # ---- validation iterator (memory.py:162-180) -------------------------------------------------
     _ITER_CHUNK = 64
@@ -359,16 +433,22 @@ class ReplayMemory:
         self._iter_base = 0
         return self
 
+    def iter_states(self, first, count):
+        """Iterator states (memory.py:166-178) for current_idx = first .. first+count-1 in one launch:
+        device float32 [count, history, 84, 84] (backward-only blanking, negative indices wrap)."""
+        self.flush_appends()
+        tr = self.transitions
+        buf = torch.empty((count, self.history, 84, 84), dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.rb_iter_states(_lib.ptr(tr.frames), _lib.ptr(tr.timestep), tr.size, int(first), int(count),
+                                            self.history, _lib.ptr(buf), _lib.stream()))
+        return buf
+
     def __next__(self):
         if self.current_idx == self.capacity:
             raise StopIteration
         if self._iter_buf is None or self.current_idx >= self._iter_base + self._iter_buf.shape[0]:
             count = min(self._ITER_CHUNK, self.capacity - self.current_idx)
-            tr = self.transitions
-            buf = torch.empty((count, self.history, 84, 84), dtype=torch.float32, device=self.device)
-            _lib.check(self._lib.rb_iter_states(_lib.ptr(tr.frames), _lib.ptr(tr.timestep), tr.size,
-                                                self.current_idx, count, self.history, _lib.ptr(buf), _lib.stream()))
-            self._iter_buf, self._iter_base = buf, self.current_idx
+            self._iter_buf, self._iter_base = self.iter_states(self.current_idx, count), self.current_idx
         state = self._iter_buf[self.current_idx - self._iter_base]
         self.current_idx += 1
         return state
@@ -377,6 +457,8 @@ class ReplayMemory:
 
     # ---- pickling (main.py:85-100 pickles the whole object) --------------------------------------
     def __getstate__(self):
+        """Own compact layout (plain numpy arrays, structure of arrays).  For a file the REFERENCE can load use
+        save_reference_pickle()."""
         self.flush_appends()
         tr = self.transitions
         return dict(
@@ -388,22 +470,84 @@ class ReplayMemory:
             action=tr.action.cpu().numpy(), reward=tr.reward.cpu().numpy(),
             nonterminal=tr.nonterminal.cpu().numpy())
 
-    def __setstate__(self, s):
-        self.device = _require_cuda(s["device"])
-        self.capacity, self.history, self.discount, self.n = s["capacity"], s["history"], s["discount"], s["n"]
-        self.priority_weight, self.priority_exponent, self.t = s["priority_weight"], s["priority_exponent"], s["t"]
-        self.rng, self.seed, self.max_attempts, self.strict = s["rng"], s["seed"], s["max_attempts"], s["strict"]
+    def _init_runtime(self, rng_counter=0):
         self.n_step_scaling = torch.tensor([self.discount ** i for i in range(self.n)], dtype=torch.float32,
                                            device=self.device)
-        self.transitions = SegmentTree(self.capacity, self.device)
-        self.transitions.load_arrays(s["sum_tree"], s["frames"], s["timestep"], s["action"], s["reward"],
-                                     s["nonterminal"], s["index"], s["full"], s["t"], s["max"])
         self.defer_appends, self._queue = False, []
-        self._rng_counter = torch.tensor([s["rng_counter"]], dtype=torch.int64, device=self.device)
+        self._rng_counter = torch.tensor([int(rng_counter)], dtype=torch.int64, device=self.device)
         self._beta_dev = torch.full((1,), float(self.priority_weight), dtype=torch.float32, device=self.device)
         self._beta_pushed = float(self.priority_weight)
         self._lib = _lib.load()
         self._last = None
+        self._stage = None
+
+    def __setstate__(self, s):
+        if "version" not in s and "transitions" in s:
+            return self._setstate_reference(s)
+        self.device = _require_cuda(s["device"])
+        self.capacity, self.history, self.discount, self.n = s["capacity"], s["history"], s["discount"], s["n"]
+        self.priority_weight, self.priority_exponent, self.t = s["priority_weight"], s["priority_exponent"], s["t"]
+        self.rng, self.seed, self.max_attempts, self.strict = s["rng"], s["seed"], s["max_attempts"], s["strict"]
+        self.transitions = SegmentTree(self.capacity, self.device)
+        self.transitions.load_arrays(s["sum_tree"], s["frames"], s["timestep"], s["action"], s["reward"],
+                                     s["nonterminal"], s["index"], s["full"], s["t"], s["max"])
+        self._init_runtime(s["rng_counter"])
+
+    def _setstate_reference(self, s):
+        """A memory file written by the REFERENCE (its ReplayMemory.__dict__, memory.py:93-102, with the AoS
+        Transition_dtype `data` and the truncated `sum_tree` of memory.py:13-20): rebuilt in HBM.  A CPU device in the
+        file is mapped to the current CUDA device (the replay has no host variant)."""
+        dev = torch.device(s.get("device", "cuda"))
+        self.device = _require_cuda(dev if dev.type == "cuda" else "cuda")
+        self.capacity, self.history, self.discount, self.n = int(s["capacity"]), int(s["history"]), s["discount"], int(s["n"])
+        self.priority_weight, self.priority_exponent, self.t = s["priority_weight"], s["priority_exponent"], int(s["t"])
+        self.rng, self.max_attempts, self.strict = "philox", 64, False
+        self.seed = int(torch.initial_seed()) & (2 ** 64 - 1)
+        tr = s["transitions"]
+        if isinstance(tr, SegmentTree):
+            tr._materialise(self.device, self.t)
+        else:   # any object carrying the reference's fields
+            fields = {k: getattr(tr, k) for k in ("index", "size", "full", "sum_tree", "data", "max")}
+            tr = SegmentTree(int(fields["size"]), self.device)
+            tr.load_arrays(**reference_fields_to_ring(fields, t=self.t))
+        self.transitions = tr
+        self._init_runtime()
+
+    def reference_state(self, device="cpu"):
+        """(ReplayMemory.__dict__, SegmentTree.__dict__) exactly as the reference's objects hold them."""
+        self.flush_appends()
+        dev = torch.device(device)
+        mem = dict(device=dev, capacity=self.capacity, history=self.history, discount=self.discount, n=self.n,
+                   priority_weight=self.priority_weight, priority_exponent=self.priority_exponent, t=self.t,
+                   n_step_scaling=self.n_step_scaling.to(dev))
+        return mem, self.transitions.__getstate__()
+
+
+def save_reference_pickle(mem, file, device="cpu", protocol=None):
+    """Write `mem` as a pickle the UNMODIFIED reference loads with pickle.load (main.py:85-91): the stream names the
+    classes `memory.ReplayMemory` / `memory.SegmentTree` and carries the reference's own field layout, so inside the
+    reference process it unpickles into the reference's classes (and, with dropin/ on the path, into ours)."""
+    import pickle
+    import sys
+    import types
+    mem_state, tree_state = mem.reference_state(device)
+    stand_in = types.ModuleType("memory")
+    tree_cls = type("SegmentTree", (), {"__module__": "memory"})
+    mem_cls = type("ReplayMemory", (), {"__module__": "memory"})
+    stand_in.SegmentTree, stand_in.ReplayMemory = tree_cls, mem_cls
+    tree = tree_cls()
+    tree.__dict__.update(tree_state)
+    obj = mem_cls()
+    obj.__dict__.update(mem_state, transitions=tree)
+    saved = sys.modules.get("memory")
+    sys.modules["memory"] = stand_in      # pickle verifies that memory.ReplayMemory is the class being written
+    try:
+        pickle.dump(obj, file, protocol=protocol)
+    finally:
+        if saved is None:
+            del sys.modules["memory"]
+        else:
+            sys.modules["memory"] = saved
 
 
 def ring_to_reference_fields(state):
@@ -423,7 +567,7 @@ def ring_to_reference_fields(state):
 def reference_fields_to_ring(fields, t=0):
     """Inverse of ring_to_reference_fields: SegmentTree attributes of the reference -> load_arrays kwargs."""
     data = fields["data"]
-    size = fields["size"]
+    size = int(fields["size"])
     return dict(sum_tree=fields["sum_tree"], frames=np.ascontiguousarray(data["state"]).reshape(size, FRAME),
                 timestep=data["timestep"], action=data["action"], reward=data["reward"],
                 nonterminal=data["nonterminal"].astype(np.uint8), index=fields["index"], full=fields["full"],

@@ -202,6 +202,7 @@ class DQN(nn.Module):
         layers = self.noisy_layers()
         self.register_buffer("_f_in", torch.cat([m._f_in for m in layers]), persistent=False)
         self.register_buffer("_f_out", torch.cat([m._f_out for m in layers]), persistent=False)
+        self._noise_queue = []   # parity facility: injected raw normals consumed by the next reset_noise() calls
         self._eps_stale = False  # weight_epsilon / bias_epsilon buffers currently equal the outer product of the factors
         self._head = None
         self.use_fused_head = True
@@ -224,10 +225,18 @@ class DQN(nn.Module):
         raw normals (parity).  Needs the network on a CUDA device."""
         if not self._f_in.is_cuda:
             raise _lib.RainbowB200Error("DQN.reset_noise needs the network on a CUDA device (no CPU fallback)")
+        if x_in is None and self._noise_queue:
+            x_in, x_out = self._noise_queue.pop(0)
         _lib.check(_lib.load().rb_noise_factors(_lib.ptr(self._f_in), self._f_in.numel(), _lib.ptr(self._f_out),
                                                 self._f_out.numel(), _lib.ptr(x_in), _lib.ptr(x_out), self.noise_seed,
                                                 _lib.ptr(self._noise_counter), _lib.stream()))
         self._eps_stale = True
+
+    def queue_noise(self, x_in, x_out):
+        """Parity testing: the next argument-less reset_noise() uses these raw standard normals (device float32, all
+        layers back to back: eps_in draws / eps_out draws, model.py:37-38) instead of the device Philox stream, so the
+        public reset_noise(); learn(mem) sequence can be fed the reference's recorded torch.randn draws."""
+        self._noise_queue.append((x_in.contiguous(), x_out.contiguous()))
 
     def materialise_noise(self):
         """Bring weight_epsilon / bias_epsilon (model.py:39-40) up to date with the factor vectors."""

@@ -33,7 +33,7 @@ def test_abi_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), "python binding table and header disagree"
     for name in declared:
         assert hasattr(lib, name), f"librainbow_b200.so does not export {name}"
-    assert lib.rb_abi_version() == 1
+    assert lib.rb_abi_version() == 2
     assert lib.rb_clip_adam_scratch_elems() > 0
 
 
@@ -42,15 +42,15 @@ def test_abi_argument_validation_without_gpu():
     from rainbow_b200 import _lib
     lib = _lib.load()
     one = C.c_void_p(8)  # never dereferenced: validation fails first
-    assert lib.rb_tree_update(None, 7, 8, one, one, 0.5, 0, 4, one, None, None) == -22
+    assert lib.rb_tree_update(None, 7, 8, one, one, 0.5, 0, 4, one, None, None, None) == -22
     assert b"null" in lib.rb_last_error()
-    assert lib.rb_tree_update(one, 7, 7, one, one, 0.5, 0, 4, one, None, None) == -22          # odd size
+    assert lib.rb_tree_update(one, 7, 7, one, one, 0.5, 0, 4, one, None, None, None) == -22          # odd size
     assert lib.rb_tree_sample(one, 7, 8, one, 3, 4, None, 0, 1, None, 4, 0.4, None, 8, one, one, one, one, one, None) == -22
     assert lib.rb_gather(one, one, one, one, one, 8, one, 4, 40, 30, one, one, one, one, one, one, None) == -34  # window > 64
     assert lib.rb_c51_loss_grad(one, one, one, one, one, one, one, one, -10.0, 10.0, 0.4, 0.97, 4, 6, 200, one, one, None,
                                 None, None) == -34                                               # atoms > 128
     assert lib.rb_noisy_resample(None, None, None, None, 4, None, None, 1, None, None) == -22
-    assert lib.rb_clip_adam(one, one, one, one, 0, 1.0, 10.0, 1e-4, 0.9, 0.999, 1e-4, one, one, None, None) == -22
+    assert lib.rb_clip_adam(one, one, one, one, 0, 1.0, 10.0, 1e-4, 0.9, 0.999, 1e-4, one, one, None, None, None) == -22
     tot, n = C.c_double(), C.c_int()
     assert lib.rb_profile_collect(99, C.byref(tot), C.byref(n)) == -22
 

@@ -417,7 +417,7 @@ def test_clip_adam_oracle():
         g = (rs.normal(0, 1, P) * scale / np.sqrt(P)).astype(np.float32)
         dg = torch.from_numpy(g).to(DEV)
         _lib.check(L.rb_clip_adam(dp.data_ptr(), dg.data_ptr(), dm.data_ptr(), dv.data_ptr(), P, 1.0, 10.0, 6.25e-5,
-                                  0.9, 0.999, 1.5e-4, step.data_ptr(), part.data_ptr(), norm.data_ptr(),
+                                  0.9, 0.999, 1.5e-4, step.data_ptr(), part.data_ptr(), norm.data_ptr(), None,
                                   torch.cuda.current_stream().cuda_stream))
         o_norm = oracle.clip_adam(p, g.copy(), m, v, 10.0, 6.25e-5, 0.9, 0.999, 1.5e-4, it)
         assert abs(float(norm.item()) - o_norm) <= 2e-6 * o_norm
