@@ -195,7 +195,8 @@ def gen_replay():
     out = {}
     cases = []
     for name, cap, n, B, fill, beta in (("c64n3", 64, 3, 8, 100, 0.4), ("c64n1", 64, 1, 8, 40, 0.7),
-                                        ("c128n20", 128, 20, 4, 300, 1.0), ("c500n3", 500, 3, 32, 700, 0.4)):
+                                        ("c128n20", 128, 20, 4, 300, 1.0), ("c500n3", 500, 3, 32, 700, 0.4),
+                                        ("c128n36", 128, 36, 4, 300, 0.5)):   # history + n = 40 > 32 window records
         rs = np.random.RandomState(11)
         np.random.seed(5)
         mem = ref_memory.ReplayMemory(make_args(multi_step=n, priority_weight=beta), cap)
@@ -319,13 +320,13 @@ def gen_learn():
     """agent.py:61-100 run unmodified on stub nets: loss, m, grad w.r.t. pre-softmax logits."""
     out = {}
     cases = []
-    for name, B, A, n, seed in (("b32a6", 32, 6, 3, 0), ("b1a3", 1, 3, 1, 1), ("b64a18", 64, 18, 20, 2),
-                                ("b8a4sharp", 8, 4, 3, 3)):
+    for name, B, A, n, seed, atoms in (("b32a6", 32, 6, 3, 0, 51), ("b1a3", 1, 3, 1, 1, 51), ("b64a18", 64, 18, 20, 2, 51),
+                                       ("b8a4sharp", 8, 4, 3, 3, 51), ("b8a4z101", 8, 4, 3, 4, 101)):   # 101 atoms: > 64
         g = torch.Generator().manual_seed(seed)
         rs = np.random.RandomState(seed)
-        args = make_args(batch_size=B, multi_step=n, norm_clip=1e9)
+        args = make_args(batch_size=B, multi_step=n, norm_clip=1e9, atoms=atoms)
         ag = ref_agent.Agent(make_args(batch_size=B, multi_step=n, norm_clip=1e9, architecture="data-efficient",
-                                       hidden_size=8), FakeEnv(A))
+                                       hidden_size=8, atoms=atoms), FakeEnv(A))
         Z = args.atoms
         scale = 6.0 if "sharp" in name else 1.5
         q_s = torch.randn(B, A, Z, generator=g) * scale
@@ -449,6 +450,127 @@ def gen_model_step():
     np.savez_compressed(os.path.join(OUT, "model_step.npz"), **out)
 
 
+# --------------------------------------------------------------------------------------------
+def sample_stride(numel):
+    """Sub-sampling rule of the full-update fixtures (tests/helpers.py holds the same function): small tensors are
+    kept whole, large ones every stride-th element (odd strides, so every row and column is hit)."""
+    return 1 if numel <= 4096 else (5 if numel <= 40000 else (23 if numel <= 200000 else 199))
+
+
+class RandnRecorder:
+    """Records every torch.randn draw (model.py:33) made while active."""
+
+    def __init__(self):
+        self.calls = []
+        self.orig = torch.randn
+
+    def __enter__(self):
+        def wrapped(*a, **k):
+            x = self.orig(*a, **k)
+            self.calls.append(x.clone())
+            return x
+
+        torch.randn = wrapped
+        return self
+
+    def __exit__(self, *a):
+        torch.randn = self.orig
+
+    def split(self):
+        """reset order is eps_in then eps_out per layer (model.py:37-38): returns (all eps_in draws, all eps_out draws)."""
+        assert len(self.calls) == 8
+        return torch.cat(self.calls[0::2]).numpy(), torch.cat(self.calls[1::2]).numpy()
+
+
+def gen_full_update(name, arch, hidden, n, cap, B, A, steps, seed):
+    """`steps` consecutive UNMODIFIED `dqn.reset_noise(); dqn.learn(mem)` pairs (main.py:150-151) at a benchmarked network
+    shape on a small real ReplayMemory: recorded noise draws, sampled indices, per-sample losses, gradients, parameters and
+    the sum tree after every step.  Initial parameters and frames are regenerated by the test from the seeds (checked by
+    SHA); large tensors are sub-sampled (sample_stride) and additionally pinned by float64 sums."""
+    out = {}
+    torch.manual_seed(seed)
+    np.random.seed(seed + 100)
+    args = make_args(batch_size=B, multi_step=n, architecture=arch, hidden_size=hidden)
+    ag = ref_agent.Agent(args, FakeEnv(A))
+    sd0 = torch.cat([p.detach().reshape(-1) for _, p in ag.online_net.named_parameters()])
+    mem = ref_memory.ReplayMemory(args, cap)
+    rs = np.random.RandomState(seed + 7)
+    fill = cap + cap // 3
+    frames = rs.randint(0, 256, (fill, 84, 84), dtype=np.uint8)     # the test re-draws exactly this
+    ep = 0
+    for i in range(fill):
+        st = torch.zeros(4, 84, 84)
+        st[-1] = (torch.from_numpy(frames[i]).float() + 0.5) / 255     # mul(255) + truncation gives back frames[i]
+        terminal = bool(rs.uniform() < 0.03) or ep > 60
+        ep = 0 if terminal else ep + 1
+        mem.append(st, int(rs.randint(0, A)), float(rs.randint(-1, 2)), terminal)
+    ts = mem.transitions.tree_start
+    mem.update_priorities(np.arange(cap) + ts, rs.uniform(0.01, 4, cap).astype(np.float32))
+    ring = np.zeros((cap, 84, 84), np.uint8)
+    for i in range(fill):
+        ring[i % cap] = frames[i]
+    assert np.array_equal(mem.transitions.data["state"], ring)
+    t = mem.transitions
+    out["ring_sum_tree"], out["ring_timestep"], out["ring_action"] = t.sum_tree.copy(), t.data["timestep"].copy(), t.data["action"].copy()
+    out["ring_reward"], out["ring_nonterminal"] = t.data["reward"].copy(), t.data["nonterminal"].astype(np.uint8)
+    out["ring_meta"] = np.array([t.index, int(t.full), mem.t, t.size], dtype=np.int64)
+    out["ring_max"] = np.float32(t.max)
+    strides = {k: sample_stride(p.numel()) for k, p in ag.online_net.named_parameters()}
+    attempts = []
+    for k in range(steps):
+        with RandnRecorder() as rec:
+            ag.reset_noise()                                            # main.py:150
+        out[f"s{k}_online_x_in"], out[f"s{k}_online_x_out"] = rec.split()
+        got = {}
+        orig_update = mem.update_priorities
+
+        def spy(idxs, pri):
+            got["idxs"], got["loss"] = np.array(idxs, copy=True), np.array(pri, copy=True)
+            return orig_update(idxs, pri)
+
+        mem.update_priorities = spy
+        try:
+            with RandnRecorder() as rec, UniformRecorder() as urec:
+                ag.learn(mem)                                           # main.py:151
+        finally:
+            del mem.update_priorities
+        out[f"s{k}_target_x_in"], out[f"s{k}_target_x_out"] = rec.split()
+        attempts.append(len(urec.calls))
+        out[f"s{k}_tidx"], out[f"s{k}_loss"] = got["idxs"].astype(np.int64), got["loss"].astype(np.float32)
+        for key, p in ag.online_net.named_parameters():
+            for kind, v in (("grad", p.grad), ("param", p.detach())):
+                flat = v.reshape(-1)
+                out[f"s{k}_{kind}.{key}"] = flat[::strides[key]].numpy().copy()
+                out[f"s{k}_{kind}sum.{key}"] = np.array([float(flat.double().sum()), float((flat.double() ** 2).sum())])
+        out[f"s{k}_tree_after"] = t.sum_tree.copy()
+        out[f"s{k}_max_after"] = np.float32(t.max)
+    np.savez_compressed(os.path.join(OUT, f"update_{name}.npz"), **out)
+    return dict(name=name, arch=arch, hidden=hidden, n=n, cap=cap, B=B, A=A, steps=steps, seed=seed, fill=fill,
+                attempts=attempts, sd0_sha=sha(sd0.numpy()), frames_sha=sha(ring), strides=strides)
+
+
+def gen_ref_pickle():
+    """A replay file written by the UNMODIFIED reference exactly like main.py:94-100 does (bz2 + pickle of the whole
+    ReplayMemory object), plus the arrays it holds, for the load-a-reference-file test."""
+    import bz2
+    import pickle
+    rs = np.random.RandomState(21)
+    mem = ref_memory.ReplayMemory(make_args(multi_step=3), 64)
+    for i in range(83):
+        mem.append(pattern_state(i), int(rs.randint(0, 6)), float(rs.randint(-1, 2)), bool(i in (6, 15, 40, 41)))
+    mem.update_priorities(np.arange(64) + mem.transitions.tree_start, rs.uniform(0.1, 3, 64).astype(np.float32))
+    with bz2.open(os.path.join(OUT, "ref_memory.pkl.bz2"), "wb") as f:
+        pickle.dump(mem, f)
+    out = {}
+    dump_ring(mem, out, "")
+    np.random.seed(3)
+    with UniformRecorder() as rec:
+        tidx, states, actions, returns, nstates, nonterm, weights = mem.sample(4)
+    out["u01"], out["tidx"], out["states"], out["returns"] = np.stack(rec.calls), np.asarray(tidx, np.int64), states.numpy(), returns.numpy()
+    out["weights"] = weights.numpy()
+    np.savez_compressed(os.path.join(OUT, "ref_memory.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     manifest = dict(reference="Kaixhin/Rainbow@1745b184c3dfc03d4ffa3ce2342ced9996b39a60", numpy=np.__version__,
@@ -460,6 +582,10 @@ def main():
     manifest["learn_cases"] = gen_learn()
     gen_noise()
     gen_model_step()
+    # whole-update trajectories at the benchmarked shapes: C2 (canonical / 512, n 3) and C3 (data-efficient / 256, n 20)
+    manifest["update_cases"] = [gen_full_update("c2", "canonical", 512, 3, 512, 32, 6, 3, 11),
+                                gen_full_update("c3", "data-efficient", 256, 20, 2048, 32, 6, 3, 12)]
+    gen_ref_pickle()
     with open(os.path.join(OUT, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1)
     for fn in sorted(os.listdir(OUT)):

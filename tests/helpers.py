@@ -49,3 +49,28 @@ def assert_bits_equal(a, b, what=""):
     else:
         bad = np.flatnonzero(a.ravel() != b.ravel())
     assert bad.size == 0, f"{what}: {bad.size} mismatches, first at {bad[:5]}: {a.ravel()[bad[:5]]} vs {b.ravel()[bad[:5]]}"
+
+
+def sample_stride(numel):
+    """Sub-sampling rule of the full-update fixtures (same function as in oracle/gen_golden.py)."""
+    return 1 if numel <= 4096 else (5 if numel <= 40000 else (23 if numel <= 200000 else 199))
+
+
+def update_case(name):
+    for c in manifest()["update_cases"]:
+        if c["name"] == name:
+            return c
+    raise KeyError(name)
+
+
+def update_case_ring(case):
+    """Frames of a full-update fixture's ring, re-drawn from the seed exactly like oracle/gen_golden.py::gen_full_update
+    does (the fixture stores only their SHA-256)."""
+    import hashlib
+    rs = np.random.RandomState(case["seed"] + 7)
+    frames = rs.randint(0, 256, (case["fill"], 84, 84), dtype=np.uint8)
+    ring = np.zeros((case["cap"], 84, 84), np.uint8)
+    for i in range(case["fill"]):
+        ring[i % case["cap"]] = frames[i]
+    assert hashlib.sha256(np.ascontiguousarray(ring).tobytes()).hexdigest() == case["frames_sha"], "frame stream differs"
+    return ring

@@ -258,3 +258,74 @@ def test_flat_parameter_layout():
     # load_state_dict writes through the views (the flat buffer follows), as update_target_net / --model rely on
     net.load_state_dict({k: v + 1 for k, v in before.items()})
     assert torch.equal(opt.flat_param[opt.offsets[0]:opt.offsets[0] + named[0][1].numel()], (before[named[0][0]] + 1).reshape(-1))
+
+
+def test_save_reference_pickle_is_loaded_by_the_unmodified_reference(tmp_path):
+    """SURVEY 8(f).3, export direction, checked against the REAL reference where it exists (the build container; the GPU box
+    has no /root/reference): save_reference_pickle() of a replay holding the fixture's arrays is read by the reference's own
+    memory.py in a fresh interpreter, and the reference's next sample reproduces the recorded one (tests/golden/ref_memory.npz
+    was produced by that same reference object)."""
+    ref = "/root/reference"
+    if not os.path.isfile(os.path.join(ref, "memory.py")):
+        pytest.skip("the reference checkout is only present in the build container")
+    from helpers import golden
+    from rainbow_b200.memory import Transition_dtype, save_reference_pickle
+    g = golden("ref_memory")
+    meta = g["meta"]
+    size = int(meta[3])
+
+    class HostReplay:   # stands in for a device ReplayMemory: same reference_state() contract, no GPU needed
+        def reference_state(self, device="cpu"):
+            data = np.zeros(size, dtype=Transition_dtype)
+            data["timestep"], data["state"] = g["timestep"], g["frames"].reshape(size, 84, 84)
+            data["action"], data["reward"], data["nonterminal"] = g["action"], g["reward"], g["nonterminal"].astype(np.bool_)
+            mem = dict(device=torch.device(device), capacity=size, history=4, discount=0.99, n=3, priority_weight=0.4,
+                       priority_exponent=0.5, t=int(meta[2]), n_step_scaling=torch.tensor([0.99 ** i for i in range(3)]))
+            tree = dict(index=int(meta[0]), size=size, full=bool(meta[1]), tree_start=2 ** (size - 1).bit_length() - 1,
+                        sum_tree=g["sum_tree"], data=data, max=float(g["max"]))
+            return mem, tree
+
+    path = tmp_path / "mem.pkl"
+    with open(path, "wb") as f:
+        save_reference_pickle(HostReplay(), f)
+    assert "memory" not in sys.modules or "rainbow_b200" not in getattr(sys.modules["memory"], "__file__", "")
+    code = (f"import sys, pickle, numpy as np; sys.path.insert(0, {ref!r}); import memory\n"
+            f"mem = pickle.load(open({str(path)!r}, 'rb'))\n"
+            "assert type(mem) is memory.ReplayMemory and type(mem.transitions) is memory.SegmentTree\n"
+            "np.random.seed(3)\n"
+            "out = mem.sample(4)\n"
+            "print('TIDX', ' '.join(str(int(i)) for i in out[0]))\n"
+            "mem.append(out[1][0], 1, 0.0, False); mem.update_priorities(out[0], np.ones(4, np.float32))\n")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stderr[-3000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("TIDX")][0]
+    assert [int(x) for x in line.split()[1:]] == g["tidx"].tolist()
+
+
+def test_oracle_clip_adam_follows_the_reference_trajectory():
+    """Pins oracle.clip_adam (the checker of rb_clip_adam) to the UNMODIFIED reference: the recorded gradients of the three
+    consecutive C2-shaped updates (tests/golden/update_c2.npz, sub-sampled tensors) driven through the oracle's clip+Adam must
+    reproduce the reference's parameters after every step to float rounding (<= 4e-9 = one ulp of the largest weights, |p| < 0.0625)."""
+    import oracle
+    from helpers import golden, update_case
+    case, g = update_case("c2"), golden("update_c2")
+    torch.manual_seed(case["seed"])
+    args = make_args(batch_size=case["B"], multi_step=case["n"], architecture=case["arch"], hidden_size=case["hidden"])
+    from rainbow_b200.model import DQN
+    net = DQN(args, case["A"])            # same host RNG stream as the reference's Agent construction (checked by SHA below)
+    import hashlib
+    sd0 = torch.cat([p.detach().reshape(-1) for _, p in net.named_parameters()]).numpy()
+    assert hashlib.sha256(sd0.tobytes()).hexdigest() == case["sd0_sha"]
+    keys = [k for k, _ in net.named_parameters()]
+    p = np.concatenate([v.detach().reshape(-1)[::case["strides"][k]].numpy() for k, v in net.named_parameters()]).astype(np.float32)
+    m, v = np.zeros_like(p), np.zeros_like(p)
+    worst = 0.0
+    for s in range(case["steps"]):
+        grad = np.concatenate([g[f"s{s}_grad.{k}"] for k in keys]).astype(np.float32)
+        total = float(np.sqrt(sum(g[f"s{s}_gradsum.{k}"][1] for k in keys)))
+        assert total < 10.0           # no clipping in the recorded steps: the sub-sample's own norm is below the threshold too
+        oracle.clip_adam(p, grad, m, v, 10.0, 6.25e-5, 0.9, 0.999, 1.5e-4, s + 1)
+        want = np.concatenate([g[f"s{s}_param.{k}"] for k in keys])
+        worst = max(worst, float(np.abs(p - want).max()))
+        p[:] = want                   # follow the reference exactly from here on (m, v stay the oracle's)
+    assert worst <= 4e-9, worst

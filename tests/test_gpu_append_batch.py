@@ -1,7 +1,4 @@
-"""GPU tests of code paths that are compiled but were not yet exercised on hardware when round 1 ran out of GPU
-budget (ReplayMemory(defer_appends=True) -> rb_append_batch).  They are skipped unless RB_TEST_EXPERIMENTAL=1, so the
-regular `-m gpu` run only covers measured code; the first thing to do with a GPU is to run them."""
-import os
+"""GPU tests of the actor-side batched append (ReplayMemory(defer_appends=True) -> rb_append_batch)."""
 
 import numpy as np
 import pytest
@@ -10,8 +7,7 @@ import torch
 from helpers import assert_bits_equal, golden
 from test_gpu_parity import DEV, cpu, make_args
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("RB_TEST_EXPERIMENTAL") != "1", reason="set RB_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("flush_every", [1, 3, 8, 100])

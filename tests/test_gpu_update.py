@@ -1,0 +1,509 @@
+"""GPU parity tests of the WHOLE update at the benchmarked shapes, and of the API surface main.py / test.py drive.
+
+ * test_full_update_vs_reference: three consecutive `dqn.reset_noise(); dqn.learn(mem)` pairs through the PUBLIC API against
+   the unmodified reference's recorded trajectory (tests/golden/update_c2.npz: canonical / 512, B 32, A 6, n 3;
+   update_c3.npz: data-efficient / 256, n 20): sampled indices bit-exact, loss <= 1e-5, gradients <= 1e-6, parameters after
+   every Adam step, priority leaves == fl32(sqrt(loss)) bit-exact, tree after the reference's write-back bit-exact.
+ * graph replay == eager (bitwise), rejected batches are skipped on the device, act()/evaluate_q graphs, reference pickle
+   interchange, data-parallel world 2, and the main.py call sequence against dropin/.
+Observed maxima are written to gpurun_out/parity_observed.json when that directory exists (evidence for DESIGN.md)."""
+import bz2
+import hashlib
+import io
+import json
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_bits_equal, golden, sample_stride, update_case, update_case_ring
+from test_gpu_parity import DEV, FakeEnv, cpu, make_args, synthetic_ring
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def record(name, values):
+    d = os.path.join(ROOT, "gpurun_out")
+    if not os.path.isdir(d):
+        return
+    path = os.path.join(d, "parity_observed.json")
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data[name] = values
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1, sort_keys=True)
+
+
+def build_update_case(name, **agent_kw):
+    """Agent + ReplayMemory in exactly the state the reference held before step 0 of the fixture."""
+    from rainbow_b200.agent import Agent
+    from rainbow_b200.memory import ReplayMemory
+    case, g = update_case(name), golden("update_" + name)
+    torch.manual_seed(case["seed"])          # same host RNG stream as the reference's Agent construction
+    args = make_args(batch_size=case["B"], multi_step=case["n"], architecture=case["arch"], hidden_size=case["hidden"],
+                     cuda_graph=False, **agent_kw)
+    ag = Agent(args, FakeEnv(case["A"]))
+    sd0 = torch.cat([p.detach().reshape(-1).cpu() for _, p in ag.online_net.named_parameters()]).numpy()
+    assert hashlib.sha256(sd0.tobytes()).hexdigest() == case["sd0_sha"], "initial parameters differ from the reference's"
+    mem = ReplayMemory(args, case["cap"], rng="numpy")
+    meta = g["ring_meta"]
+    mem.transitions.load_arrays(g["ring_sum_tree"], update_case_ring(case).reshape(case["cap"], -1), g["ring_timestep"],
+                                g["ring_action"], g["ring_reward"], g["ring_nonterminal"], int(meta[0]), bool(meta[1]),
+                                int(meta[2]), float(g["ring_max"]))
+    mem.t = int(meta[2])
+    return case, g, ag, mem
+
+
+@pytest.mark.parametrize("name", ["c2", "c3"])
+def test_full_update_vs_reference(name):
+    case, g, ag, mem = build_update_case(name)
+    np.random.seed(case["seed"] + 100)       # the stream the reference's mem.sample consumed (memory.py:129)
+    on, tg, tr = ag.online_net, ag.target_net, mem.transitions
+    obs = dict(loss=0.0, grad=0.0, param=0.0, param_rel_update=0.0, sums=0.0)
+    bad = []          # float tolerances are collected and asserted together, so one run reports every excess
+
+    def close(a, b, atol, what):
+        d = float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max())
+        if not d <= atol:
+            bad.append(f"{what}: max |diff| {d:.3e} > {atol:.1e}")
+
+    try:
+        for k in range(case["steps"]):
+            on.queue_noise(t(g[f"s{k}_online_x_in"]), t(g[f"s{k}_online_x_out"]))
+            ag.reset_noise()                                                       # main.py:150
+            tg.queue_noise(t(g[f"s{k}_target_x_in"]), t(g[f"s{k}_target_x_out"]))
+            tree_before = tr.tree.clone()
+            max_before = tr.running_max.clone()
+            prev = {key: cpu(p).reshape(-1)[::case["strides"][key]].copy() for key, p in on.named_parameters()}
+            ag.learn(mem)                                                          # main.py:151
+            torch.cuda.synchronize()
+            assert not tg._noise_queue and not on._noise_queue
+            # ---- sampling through the public API reproduces the reference's index stream -------------------------------
+            tidx = cpu(mem._last.tree_idx)
+            assert np.array_equal(tidx, g[f"s{k}_tidx"]), f"step {k}: sampled indices differ"
+            # ---- loss (north star: 1e-5) ----------------------------------------------------------------------------------
+            loss = cpu(ag.last_loss)
+            obs["loss"] = max(obs["loss"], float(np.abs(loss - g[f"s{k}_loss"]).max()))
+            close(loss, g[f"s{k}_loss"], 1e-5, f"step {k} loss")
+            # ---- A15: the priority written for every sampled leaf is fl32(sqrt(loss)) of OUR loss, bit for bit -------------
+            tree = cpu(tr.tree)
+            assert len(set(tidx.tolist())) == len(tidx)
+            assert_bits_equal(tree[tidx], np.sqrt(loss.astype(np.float32)), f"step {k}: leaf != sqrt(loss)")
+            par = np.arange((tree.size - 1) // 2)
+            assert np.array_equal(tree[par], tree[2 * par + 1] + tree[2 * par + 2]), "sum-tree invariant"
+            # ---- gradients (conv + head), parameters after the Adam step ---------------------------------------------------
+            for key, p in on.named_parameters():
+                st = case["strides"][key]
+                assert st == sample_stride(p.numel())
+                gr = cpu(p.grad).reshape(-1)
+                ref = g[f"s{k}_grad.{key}"]
+                obs["grad"] = max(obs["grad"], float(np.abs(gr[::st] - ref).max()))
+                close(gr[::st], ref, 1e-6, f"step {k} grad {key}")
+                s1, s2 = g[f"s{k}_gradsum.{key}"]
+                obs["sums"] = max(obs["sums"], abs(float((gr.astype(np.float64) ** 2).sum()) - s2) / max(s2, 1e-30))
+                assert abs(float(gr.astype(np.float64).sum()) - s1) <= 1e-6 * gr.size ** 0.5 + 1e-5 * abs(s1), f"step {k} grad sum {key}"
+                assert abs(float((gr.astype(np.float64) ** 2).sum()) - s2) <= 2e-4 * s2 + 1e-12, f"step {k} grad sq sum {key}"
+                pv = cpu(p).reshape(-1)
+                ref = g[f"s{k}_param.{key}"]
+                d = float(np.abs(pv[::st] - ref).max())
+                obs["param"] = max(obs["param"], d)
+                upd = float(np.abs(ref - prev[key]).max())
+                obs["param_rel_update"] = max(obs["param_rel_update"], d / max(upd, 1e-12))
+                # an Adam step moves a weight by at most ~lr = 6.25e-5; the GPU result must sit within 1e-7 absolute
+                # (0.16 % of the step, the reference-vs-GPU gradient noise amplified by 1/(sqrt(v)+eps)) of the reference's
+                close(pv[::st], ref, 1e-7, f"step {k} param {key}")
+                assert abs(float(pv.astype(np.float64).sum()) - g[f"s{k}_paramsum.{key}"][0]) <= 2e-7 * pv.size
+            assert int(ag.optimiser.step_count.item()) == k + 1
+            # ---- tree after the REFERENCE's write-back (same leaves, the reference's losses): bit-exact, incl. the running max ---
+            tr.tree.copy_(tree_before)
+            tr.running_max.copy_(max_before)
+            mem.update_priorities(g[f"s{k}_tidx"], g[f"s{k}_loss"])
+            torch.cuda.synchronize()
+            assert_bits_equal(cpu(tr.tree), g[f"s{k}_tree_after"], f"step {k}: tree after write-back")
+            assert np.float32(tr.max) == g[f"s{k}_max_after"]
+        assert not bad, "\n".join(bad)
+    finally:
+        record("full_update_" + name, obs)
+
+
+def _trajectory(use_graph, steps=7):
+    from rainbow_b200.agent import Agent
+    torch.manual_seed(5)
+    args = make_args(cuda_graph=use_graph, batch_size=32)
+    mem, _ = synthetic_ring(8192, seed=3, args=dict())
+    mem.seed = 99     # Philox key of the sampling stream (the counter starts at 0 in both runs)
+    ag = Agent(args, FakeEnv(6))
+    losses = []
+    for _ in range(steps):
+        ag.reset_noise()
+        ag.learn(mem)
+        losses.append(ag.last_loss.clone())
+    torch.cuda.synchronize()
+    assert (ag._graph is not None) == use_graph
+    return ag.optimiser.flat_param.clone(), mem.transitions.tree.clone(), torch.stack(losses), ag.optimiser.exp_avg_sq.clone()
+
+
+def test_graph_replay_equals_eager_bitwise():
+    """Same seeds, same Philox counters: 2 eager warm-up updates + capture + 4 replays must leave parameters, Adam moments,
+    priorities and losses bit-identical to 7 eager updates (the side-stream write-back and the concurrent branches of the
+    captured graph must not race with anything).  cuDNN is pinned to its deterministic algorithms for the comparison."""
+    old = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True
+    try:
+        pe, te, le, ve = _trajectory(False)
+        pg, tg_, lg, vg = _trajectory(True)
+    finally:
+        torch.backends.cudnn.deterministic = old
+    assert torch.equal(le, lg), "per-sample losses differ between graph replay and eager"
+    assert torch.equal(te, tg_), "sum trees differ"
+    assert torch.equal(ve, vg) and torch.equal(pe, pg), "parameters / moments differ"
+
+
+@pytest.mark.parametrize("use_graph", [False, True], ids=["eager", "graph"])
+def test_rejected_batch_is_skipped_on_device(use_graph):
+    """All priorities zero: every draw fails memory.py:131 (prob != 0).  The reference would redraw forever; here the batch
+    is rejected after max_attempts, its weights are zero and neither the parameters, the Adam state nor the tree move."""
+    from rainbow_b200.agent import Agent
+    from rainbow_b200.memory import ReplayMemory
+    torch.manual_seed(1)
+    args = make_args(cuda_graph=use_graph, architecture="data-efficient", hidden_size=64, batch_size=8)
+    mem = ReplayMemory(args, 256, max_attempts=3, seed=4)
+    tr = mem.transitions
+    tr.load_arrays(timestep=np.arange(256) % 50, action=np.zeros(256), reward=np.ones(256), nonterminal=np.ones(256), index=10,
+                   full=True, t_episode=11)
+    tr.frames.fill_(7)
+    ag = Agent(args, FakeEnv(4))
+    w0, m0 = ag.optimiser.flat_param.clone(), ag.optimiser.exp_avg.clone()
+    for _ in range(5):
+        ag.reset_noise()
+        ag.learn(mem)
+    torch.cuda.synchronize()
+    ws = mem._last
+    st = cpu(ws.status)
+    assert st[0] == 0 and st[1] == 3 and st[2] >= 1, st
+    assert float(ws.weights.abs().max()) == 0.0
+    assert torch.isfinite(ag.last_loss).all()
+    assert torch.equal(w0, ag.optimiser.flat_param) and torch.equal(m0, ag.optimiser.exp_avg)
+    assert int(ag.optimiser.step_count.item()) == 0
+    assert float(tr.tree.abs().max()) == 0.0 and tr.max == 1.0
+    assert mem.rejected_batches() >= 1
+    with pytest.raises(Exception):
+        mem.check_last_sample()
+    # ... and a valid ring trains again with the same objects
+    tr.update(np.arange(256) + tr.tree_start, np.full(256, 0.5, np.float32))
+    ag.reset_noise()
+    ag.learn(mem)
+    torch.cuda.synchronize()
+    assert not torch.equal(w0, ag.optimiser.flat_param) and int(ag.optimiser.step_count.item()) == 1
+
+
+@pytest.mark.parametrize("arch,hidden,A", [("canonical", 512, 6), ("data-efficient", 64, 3)])
+def test_act_and_evaluate_q_graphs(arch, hidden, A):
+    """agent.py:53-55 / 110-112 through the captured one-state graph and the batched path vs plain torch ops."""
+    from rainbow_b200.agent import Agent
+    torch.manual_seed(2)
+    ag = Agent(make_args(architecture=arch, hidden_size=hidden), FakeEnv(A))
+    mem, _ = synthetic_ring(512, seed=5, args=dict())
+    states = mem.iter_states(0, 40)
+    for mode in ("train", "eval", "train"):
+        getattr(ag, mode)()
+        ag.reset_noise()
+        on = ag.online_net
+        with torch.no_grad():
+            on.materialise_noise()
+            x = on.features(states)
+            w = lambda m: (torch.addcmul(m.weight_mu, m.weight_sigma, m.weight_epsilon), torch.addcmul(m.bias_mu, m.bias_sigma, m.bias_epsilon)) \
+                if on.training else (m.weight_mu, m.bias_mu)
+            lin = lambda m, v: torch.nn.functional.linear(v, *w(m))
+            v = lin(on.fc_z_v, torch.relu(lin(on.fc_h_v, x))).view(-1, 1, 51)
+            a = lin(on.fc_z_a, torch.relu(lin(on.fc_h_a, x))).view(-1, A, 51)
+            q = (torch.softmax(v + a - a.mean(1, keepdim=True), 2) * ag.support).sum(2)      # agent.py:55
+        want_a, want_q = cpu(q.argmax(1)), cpu(q.max(1)[0])
+        gap = np.sort(cpu(q), 1)
+        clear = (gap[:, -1] - gap[:, -2]) > 1e-5                                           # ignore numerical ties
+        got_a = np.array([ag.act(states[i]) for i in range(8)])                            # warm-up, capture, replays
+        got_q = np.array([ag.evaluate_q(states[i]) for i in range(8)])
+        assert np.array_equal(got_a[clear[:8]], want_a[:8][clear[:8]])
+        np.testing.assert_allclose(got_q, want_q[:8], rtol=0, atol=2e-5)
+        qa = torch.empty((40, A), device=DEV)
+        ba, bq = ag.q_select(states, q_out=qa)
+        assert np.array_equal(cpu(ba)[clear], want_a[clear])
+        np.testing.assert_allclose(cpu(bq), want_q, rtol=0, atol=2e-5)
+        np.testing.assert_allclose(cpu(qa), cpu(q), rtol=0, atol=2e-5)
+        assert isinstance(ag.act(states[3]), int) and isinstance(ag.evaluate_q(states[3]), float)
+    vals = ag.evaluate_q_memory(mem, chunk=100)
+    assert len(vals) == 512
+    np.testing.assert_allclose(vals[:40], cpu(ag.evaluate_q_batch(states)), rtol=0, atol=1e-6)
+
+
+def _dropin_modules():
+    """Import `memory` the way the unmodified main.py would with dropin/ first on sys.path."""
+    d = os.path.join(ROOT, "dropin")
+    for m in ("memory", "agent", "model"):
+        sys.modules.pop(m, None)
+    sys.path.insert(0, d)
+    try:
+        import agent
+        import memory
+    finally:
+        sys.path.remove(d)
+    return memory, agent
+
+
+def test_load_memory_file_written_by_the_reference():
+    """main.py:85-91 load_memory on a bz2 pickle the UNMODIFIED reference wrote (tests/golden/ref_memory.pkl.bz2):
+    with dropin/ shadowing `memory`, pickle.load must hand back a device-resident ReplayMemory with the same content."""
+    from rainbow_b200.memory import ReplayMemory, _SampleWorkspace
+    memory, _ = _dropin_modules()
+    try:
+        with bz2.open(os.path.join(ROOT, "tests", "golden", "ref_memory.pkl.bz2"), "rb") as f:
+            mem = pickle.load(f)
+    finally:
+        sys.modules.pop("memory", None)
+        sys.modules.pop("agent", None)
+        sys.modules.pop("model", None)
+    g = golden("ref_memory")
+    assert isinstance(mem, ReplayMemory) and mem.device.type == "cuda"
+    tr = mem.transitions
+    assert_bits_equal(tr.sum_tree, g["sum_tree"], "tree")
+    assert np.array_equal(cpu(tr.frames), g["frames"]) and np.array_equal(cpu(tr.timestep), g["timestep"])
+    assert np.array_equal(cpu(tr.action), g["action"]) and np.array_equal(cpu(tr.reward), g["reward"])
+    assert np.array_equal(cpu(tr.nonterminal), g["nonterminal"])
+    meta = g["meta"]
+    assert (tr.index, tr.full, mem.t, tr.size) == (int(meta[0]), bool(meta[1]), int(meta[2]), int(meta[3]))
+    assert list(cpu(tr.ring_state)[:3]) == [int(meta[0]), int(meta[1]), int(meta[2])] and np.float32(tr.max) == g["max"]
+    # the reference's next sample (recorded uniforms) comes out of the loaded object
+    ws = _SampleWorkspace(4, mem.history, mem.device)
+    u = g["u01"]
+    mem._launch_sample(ws, u01=t(u), attempts=u.shape[0])
+    mem._launch_gather(ws)
+    torch.cuda.synchronize()
+    assert int(ws.status[0]) == 1 and np.array_equal(cpu(ws.tree_idx), g["tidx"])
+    assert_bits_equal(cpu(ws.states), g["states"], "states")
+    np.testing.assert_allclose(cpu(ws.returns), g["returns"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(cpu(ws.weights), g["weights"], rtol=3e-7, atol=0)
+    # and it keeps working as a replay: append + sample
+    mem.append(torch.rand(4, 84, 84, device=DEV), 1, 0.0, False)
+    mem.sample(4)
+
+
+def test_save_reference_pickle_round_trip():
+    """save_reference_pickle writes the reference's own object layout (class names memory.ReplayMemory / memory.SegmentTree,
+    AoS Transition_dtype `data`, truncated sum_tree): read back through dropin/ it must reproduce the replay, and the raw
+    stream must not mention rainbow_b200 (the reference process has no such module)."""
+    from rainbow_b200.memory import ReplayMemory, save_reference_pickle
+    mem, _ = synthetic_ring(64, seed=8, args=dict(multi_step=5))
+    for i in range(9):
+        mem.append(torch.rand(4, 84, 84, device=DEV), i % 6, float(i % 3 - 1), i == 4)
+    buf = io.BytesIO()
+    save_reference_pickle(mem, buf)
+    raw = buf.getvalue()
+    assert b"rainbow_b200" not in raw and b"memory" in raw and b"ReplayMemory" in raw and b"SegmentTree" in raw
+    _dropin_modules()
+    try:
+        back = pickle.loads(raw)
+    finally:
+        for m in ("memory", "agent", "model"):
+            sys.modules.pop(m, None)
+    assert isinstance(back, ReplayMemory)
+    assert_bits_equal(back.transitions.sum_tree, mem.transitions.sum_tree, "tree")
+    for k in ("state", "timestep", "action", "reward", "nonterminal"):
+        assert np.array_equal(back.transitions.data[k], mem.transitions.data[k]), k
+    assert (back.transitions.index, back.transitions.full, back.t, back.n, back.capacity) == (mem.transitions.index, True, mem.t, 5, 64)
+    assert back.transitions.max == mem.transitions.max
+    # the compact native format still round-trips too
+    again = pickle.loads(pickle.dumps(mem))
+    assert_bits_equal(again.transitions.sum_tree, mem.transitions.sum_tree, "tree (native pickle)")
+
+
+_DP_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+from rainbow_b200.dist import GradSync, init_from_env, shard_seed
+ngpu = torch.cuda.device_count()
+backend = "nccl" if ngpu >= 2 else "gloo"          # one GPU: both ranks share it, gloo moves the CUDA tensors
+if backend == "gloo":
+    os.environ["LOCAL_RANK"] = "0"
+rank, world, local = init_from_env(backend)
+from test_gpu_parity import FakeEnv, make_args, synthetic_ring
+from rainbow_b200.agent import Agent
+dev = torch.device("cuda", local)
+torch.cuda.set_device(dev)
+def same_everywhere(x, what, expect=True):
+    a = x.detach().to(dev, torch.float64)
+    lo, hi = a.clone(), a.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi) == expect, what
+torch.manual_seed(7)                                # ONE torch seed on every rank (what a torchrun launch gives) ...
+args = make_args(device=dev, cuda_graph=False, architecture="data-efficient", hidden_size=64, batch_size=8)
+mem, _ = synthetic_ring(1024, seed=10, device=str(dev), args=dict(device=dev))   # ... identical rings ...
+same_everywhere(torch.tensor([mem.seed % (2 ** 52)]), "ranks share one sampling seed", expect=False)   # ... distinct Philox keys
+torch.manual_seed(100 + rank)                       # different initial weights per rank: the broadcast must fix that
+ag = Agent(args, FakeEnv(4))
+assert ag.sync.enabled and ag.sync.world_size == 2
+same_everywhere(ag.optimiser.flat_param, "initial parameters differ across ranks")
+# record what goes INTO every gradient all-reduce of one update and what comes out
+pre, orig = [], ag.sync.all_reduce_
+def spy(tg):
+    off = (tg.data_ptr() - ag.optimiser.flat_grad.data_ptr()) // 4
+    pre.append((off, tg.numel(), tg.detach().clone()))
+    return orig(tg)
+ag.sync.all_reduce_ = spy
+ag.reset_noise(); ag.learn(mem)
+torch.cuda.synchronize()
+ag.sync.all_reduce_ = orig
+assert sum(n for _, n, _ in pre) == ag.optimiser.numel, "the slices exchanged do not cover the flat gradient"
+for off, n, mine in pre:
+    other = mine.clone()
+    dist.all_reduce(other)                           # mine + the other rank's
+    assert torch.equal(ag.optimiser.flat_grad[off:off + n], other), "reduced gradient != sum of the per-rank gradients"
+for _ in range(4):
+    ag.reset_noise(); ag.learn(mem)
+torch.cuda.synchronize()
+assert int(ag.optimiser.step_count.item()) == 5
+same_everywhere(ag.optimiser.flat_param, "parameters diverged after 5 data-parallel updates")
+same_everywhere(ag.optimiser.exp_avg_sq, "Adam state diverged")
+same_everywhere(mem._last.tree_idx, "ranks sampled identical batches (their replay streams must differ)", expect=False)
+dist.barrier()
+dist.destroy_process_group()
+print(f"rank{rank}ok backend={backend}", flush=True)
+"""
+
+
+def test_two_rank_data_parallel_update(tmp_path):
+    """SURVEY 8(e) on hardware: torchrun world 2 (NCCL when the box has two GPUs, otherwise both ranks on this GPU with
+    gloo carrying the CUDA tensors): initial broadcast, reduced gradient == sum of the per-rank gradients for every slice
+    exchanged, parameters and Adam state bit-identical across ranks after 5 updates, replay streams per rank differ."""
+    script = tmp_path / "dp_worker.py"
+    script.write_text(_DP_WORKER)
+    port = 29700 + os.getpid() % 200
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script), ROOT]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.stdout.count("ok backend=") == 2, out.stdout
+
+
+class _StubEnv:
+    """Stands in for env.py's Env (ALE is not in the image): random frame stacks on the device, episodes of ~40 steps."""
+
+    def __init__(self, device, actions=6, seed=0):
+        self.device, self.n, self.t = device, actions, 0
+        self.gen = torch.Generator(device=device).manual_seed(seed)
+
+    def action_space(self):
+        return self.n
+
+    def _obs(self):
+        return torch.rand((4, 84, 84), device=self.device, generator=self.gen)
+
+    def reset(self):
+        self.t = 0
+        return self._obs()
+
+    def step(self, action):
+        assert 0 <= int(action) < self.n
+        self.t += 1
+        return self._obs(), float((self.t % 7 == 0) - (self.t % 11 == 0)) * 3.0, self.t >= 40
+
+    def train(self):
+        pass
+
+    def eval(self):
+        pass
+
+
+def test_main_py_call_sequence_against_dropin(tmp_path):
+    """The call sequence of the reference's main.py:103-182 (+ test.py:37-41), statement for statement, against the classes
+    the unmodified main.py would import with dropin/ on its path: validation memory filled with action -1, beta annealing
+    through the plain attribute, act/append every step, reset_noise + learn every replay_frequency steps, evaluation with
+    eval()/train() toggling, save_memory (bz2 pickle), update_target_net, save + resume from model.pth and the memory file."""
+    memory, agent = _dropin_modules()
+    try:
+        Agent, ReplayMemory = agent.Agent, memory.ReplayMemory
+        np.random.seed(123)
+        torch.manual_seed(np.random.randint(1, 10000))                                   # main.py:64-65
+        args = make_args(architecture="data-efficient", hidden_size=64, batch_size=16, T_max=400, learn_start=80,
+                         replay_frequency=4, target_update=60, evaluation_interval=120, evaluation_size=50, reward_clip=1,
+                         checkpoint_interval=200, memory_capacity=2048, memory=str(tmp_path / "mem.bz2"), disable_bzip_memory=False)
+        env = _StubEnv(args.device)
+        env.train()
+        action_space = env.action_space()
+        dqn = Agent(args, env)                                                           # main.py:109
+        mem = ReplayMemory(args, args.memory_capacity)                                   # main.py:121
+        priority_weight_increase = (1 - args.priority_weight) / (args.T_max - args.learn_start)
+        val_mem = ReplayMemory(args, args.evaluation_size)                               # main.py:127
+        T, done = 0, True
+        while T < args.evaluation_size:                                                  # main.py:128-136
+            if done:
+                state = env.reset()
+            next_state, _, done = env.step(np.random.randint(0, action_space))
+            val_mem.append(state, -1, 0.0, done)
+            state = next_state
+            T += 1
+        results_dir = str(tmp_path)
+        dqn.train()
+        done, learns, evals, target_syncs = True, 0, [], 0
+        for T in range(1, args.T_max + 1):                                               # main.py:146-182
+            if done:
+                state = env.reset()
+            if T % args.replay_frequency == 0:
+                dqn.reset_noise()
+            action = dqn.act(state)
+            next_state, reward, done = env.step(action)
+            if args.reward_clip > 0:
+                reward = max(min(reward, args.reward_clip), -args.reward_clip)
+            mem.append(state, action, reward, done)
+            if T >= args.learn_start:
+                mem.priority_weight = min(mem.priority_weight + priority_weight_increase, 1)
+                if T % args.replay_frequency == 0:
+                    dqn.learn(mem)
+                    learns += 1
+                if T % args.evaluation_interval == 0:
+                    dqn.eval()
+                    T_Qs = [dqn.evaluate_q(s) for s in val_mem]                          # test.py:37-41
+                    assert len(T_Qs) == args.evaluation_size and all(isinstance(q, float) and np.isfinite(q) for q in T_Qs)
+                    np.testing.assert_allclose(T_Qs, dqn.evaluate_q_memory(val_mem), rtol=0, atol=1e-6)
+                    evals.append(sum(T_Qs) / len(T_Qs))
+                    dqn.train()
+                    with bz2.open(args.memory, "wb") as f:                               # main.py:94-100 save_memory
+                        pickle.dump(mem, f)
+                if T % args.target_update == 0:
+                    dqn.update_target_net()
+                    target_syncs += 1
+                if (args.checkpoint_interval != 0) and (T % args.checkpoint_interval == 0):
+                    dqn.save(results_dir, "checkpoint.pth")
+            state = next_state
+        torch.cuda.synchronize()
+        assert learns == 81 and len(evals) == 3 and target_syncs == 5
+        assert int(dqn.optimiser.step_count.item()) == learns and torch.isfinite(dqn.last_loss).all()
+        assert abs(mem.priority_weight - 1.0) < 1e-9 and abs(float(mem._beta_dev.item()) - 1.0) < 1e-6
+        assert mem.rejected_batches() == 0 and mem.transitions.index == args.T_max
+        assert cpu(val_mem.transitions.action).tolist() == [-1] * args.evaluation_size
+        # resume (main.py:111-118): model.pth through args.model, the memory through load_memory
+        args2 = make_args(**{**vars(args), "model": os.path.join(results_dir, "checkpoint.pth")})
+        dqn2 = Agent(args2, env)
+        sd = torch.load(args2.model, map_location="cpu")
+        for k, v in dqn2.online_net.state_dict().items():
+            if "epsilon" not in k:
+                assert torch.equal(v.cpu(), sd[k]), k
+        with bz2.open(args.memory, "rb") as f:
+            mem2 = pickle.load(f)
+        assert isinstance(mem2, ReplayMemory) and mem2.transitions.index == 360 and mem2.capacity == args.memory_capacity
+        dqn2.reset_noise()
+        dqn2.learn(mem2)
+        with pytest.raises(FileNotFoundError):
+            Agent(make_args(**{**vars(args), "model": str(tmp_path / "missing.pth")}), env)
+    finally:
+        for m in ("memory", "agent", "model"):
+            sys.modules.pop(m, None)
