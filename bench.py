@@ -182,22 +182,67 @@ def run_cpu_port(cfg, updates, warmup, with_appends, seed=1, budget_s=None):
     return done / dt, dt, torch.get_num_threads(), done
 
 
+def run_cpu_reference(cfg, updates, warmup, budget_s, also_gpu=None):
+    """The UNMODIFIED reference (oracle/_ref, `make -C oracle _ref`) on this box's host cores, same synthetic workload:
+    returns (updates/s, seconds, threads, updates done, extra) or None when oracle/_ref is not there.  `also_gpu`: a CUDA
+    device -> additionally time the reference's own GPU path (args.device = cuda, eager PyTorch, host numpy replay) on the
+    same replay object for `extra["reference_gpu_path"]`."""
+    import torch
+
+    from oracle import ref_arm
+    if not ref_arm.available():
+        return None
+    torch.set_num_threads(host_threads())
+    log(f"reference arm: os.cpu_count={os.cpu_count()} usable threads={host_threads()} torch threads={torch.get_num_threads()}")
+    torch.manual_seed(0)
+    np.random.seed(123)
+    sess = ref_arm.Session(make_args(cfg, torch.device("cpu")), ACTIONS, cfg["cap"], synthetic_meta(cfg["cap"], 1), log=log)
+    ups, dt, done = sess.time("cpu", updates, warmup, with_appends=True, replay_frequency=REPLAY_FREQUENCY, budget_s=budget_s)
+    log(f"reference arm (cpu): {done} updates in {dt:.1f}s")
+    extra = {}
+    if also_gpu is not None:
+        flags = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = True, False, False  # torch's stock settings
+        try:
+            g_ups, g_dt, g_done = sess.time(also_gpu, 200, 5, with_appends=True, replay_frequency=REPLAY_FREQUENCY, budget_s=12)
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = flags
+        log(f"reference arm (cuda, eager): {g_done} updates in {g_dt:.1f}s")
+        extra["reference_gpu_path"] = {"value": g_ups, "unit": "updates/s", "ms_per_step": 1e3 * g_dt / g_done,
+                                       "what": f"the unmodified reference with args.device=cuda (eager PyTorch, stock torch flags, numpy sum tree on the host, "
+                                               f"per-update H2D of the batch and D2H of the losses), {g_done} updates each preceded by {REPLAY_FREQUENCY} appends"}
+    return ups, dt, torch.get_num_threads(), done, extra
+
+
+def cpu_arm(cfg, updates, warmup, budget_s, also_gpu=None):
+    """(value, seconds, threads, updates done, kind, sample text, extra): the reference itself when it travelled with the
+    snapshot (oracle/_ref), otherwise the oracle port."""
+    r = run_cpu_reference(cfg, updates, warmup, budget_s, also_gpu)
+    if r is not None:
+        ups, dt, threads, done, extra = r
+        return ups, dt, threads, done, "reference", (
+            f"{done} updates of the same workload (each preceded by {REPLAY_FREQUENCY} appends) after {warmup} warm-up updates, {dt:.1f} s; "
+            f"UNMODIFIED reference modules (oracle/_ref: memory.py, agent.py, model.py, sha256-checked copies) on torch-CPU with "
+            f"{threads} threads; the 1M-record replay object is assembled without the reference's 242 s list constructor"), extra
+    ups, dt, threads, done = run_cpu_port(cfg, updates, warmup, with_appends=True, budget_s=budget_s)
+    return ups, dt, threads, done, "port", (
+        f"{done} updates of the same workload (each preceded by {REPLAY_FREQUENCY} appends) after {warmup} warm-up updates, {dt:.1f} s; "
+        f"oracle port (oracle/_ref absent): replay tree/gather in C, nets in torch-CPU with {threads} threads"), {}
+
+
 def reference_arm(opts, cfg, rank):
-    """--impl reference: CPU arm.  The reference is pure Python and /root/reference does not exist on the GPU
-    box, so this times the oracle port (oracle/learner.py + oracle/rb_oracle.c), kind = "port"."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores (the unmodified modules
+    from oracle/_ref when present -- kind "reference" --, else the oracle port -- kind "port")."""
     if rank != 0:
         return
     per_step = 1  # one update (preceded by its 4 appends) per bench "step", exactly like our arm's e2e step
-    ups, dt, threads, total = run_cpu_port(cfg, opts.steps * per_step, min(5, max(3, opts.warmup)), with_appends=True, budget_s=150)
+    ups, dt, threads, total, kind, sample, _ = cpu_arm(cfg, opts.steps * per_step, min(5, max(3, opts.warmup)), budget_s=150)
     line = {"impl": "reference", "metric": "learner updates/sec (batch32, 1M buffer, 51 atoms)", "value": ups,
             "unit": "updates/s", "n_gpus": opts.gpus, "steps": opts.steps, "warmup": opts.warmup,
             "ms_per_step": 1e3 * dt / total, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "gpu_launches": 0,
             "config": workload_config(opts.config, cfg, opts.gpus),
-            "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": threads, "kind": "port",
-                             "sample": f"{total} updates ({per_step} per bench step), each preceded by {REPLAY_FREQUENCY} appends, "
-                                       f"after {min(5, max(3, opts.warmup))} warm-up updates; replay tree/gather in C (oracle), nets in torch-CPU "
-                                       f"with {threads} threads"},
+            "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -238,6 +283,16 @@ def algorithmic_bytes(cfg, P, noisy_elems):
     }
 
 
+def csrc_sha256():
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "rainbow_b200", "csrc")
+    for fn in sorted(os.listdir(d)):
+        if fn.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, fn), "rb").read())
+    return h.hexdigest()
+
+
 def ours(opts, cfg, rank, world, local):
     import torch
 
@@ -256,7 +311,9 @@ def ours(opts, cfg, rank, world, local):
     args = make_args(cfg, dev, peer_optimizer=opts.peer_optimizer)
     cap, B = cfg["cap"], cfg["B"]
 
-    mem = ReplayMemory(args, cap, seed=shard_seed(17, rank))
+    # defer_appends: the e2e loop's 4 appends per update are written by ONE rb_append_batch launch that reads the frames in
+    # place from the replay's pinned staging ring; the `value` loop never appends, so it is unaffected
+    mem = ReplayMemory(args, cap, seed=shard_seed(17, rank), defer_appends=True)
     meta = synthetic_meta(cap, 1 + rank)
     tr = mem.transitions
     tr.load_arrays(timestep=meta["timestep"], action=meta["action"], reward=meta["reward"], nonterminal=meta["nonterminal"],
@@ -368,8 +425,9 @@ def ours(opts, cfg, rank, world, local):
     agent.use_cuda_graph = False
     for _ in range(3):
         step()
+    timed_steps = min(K, 100)
     with _lib.KernelTimer() as kt:
-        for i in range(min(K, 100)):
+        for i in range(timed_steps):
             for j in range(REPLAY_FREQUENCY if i % 10 == 0 else 0):
                 mem.append(host_frames[j], j, 0.0, False)
             step()
@@ -387,25 +445,39 @@ def ours(opts, cfg, rank, world, local):
     P = agent.optimiser.numel
     noisy = sum(m.weight_epsilon.numel() + m.bias_epsilon.numel() for m in agent.online_net.noisy_layers())
     alg = algorithmic_bytes(cfg, P, noisy)
-    launches_per_step = {"noise_factors": 2, "tree_sample": 1, "gather": 1, "head_fc1": 2, "head_fc2": 2, "c51_dueling": 1,
-                         "head_wgrad2": 1, "head_dh": 1, "head_bwd1": 1, "bias_grad": 3, "sqnorm": 1, "clip_adam": 1,
-                         "tree_update": 1}
+    # launches per update of every hand-written kernel, counted in the eager pass above (appends excluded: they belong to
+    # the e2e loop's actor side, not to `reset_noise(); learn(mem)`)
+    launches_per_step = {k: cnt / timed_steps for k, (cnt, _) in kt.result.items() if k != "append"}
     kernels = {}
     for name, (cnt, us) in kt.result.items():
         if name in alg:
             gbs = alg[name] / (us * 1e-6) / 1e9
             kernels[name] = {"us": round(us, 2), "bytes": alg[name], "GBps": round(gbs, 1), "frac": round(gbs / peak, 4),
-                             "launches_timed": cnt}
-    step_kernel_us = {k: kernels[k]["us"] * launches_per_step.get(k, 0) for k in kernels}
-    # dominant hand-written kernel = the longest single launch of the step (it also moves the most bytes)
-    dominant = max((k for k in kernels if launches_per_step.get(k, 0)), key=lambda k: kernels[k]["us"])
+                             "launches_timed": cnt, "launches_per_step": round(launches_per_step.get(name, 0), 2)}
+    step_kernel_us = {k: kt.result[k][1] * n for k, n in launches_per_step.items()}
+    # dominant hand-written kernel = the one the step spends the most device time in (duration x launches per update);
+    # the longest single launch is reported next to it
+    ranked = [k for k in sorted(step_kernel_us, key=step_kernel_us.get, reverse=True) if k in kernels]
+    dominant = ranked[0]
+    longest = max((k for k in kernels if launches_per_step.get(k, 0)), key=lambda k: kernels[k]["us"])
     d = kernels[dominant]
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu --set full capture
+    # DRAM bytes per launch come from the committed `ncu --set full` capture; they are only quoted while the kernel sources
+    # are the ones that capture was taken from (sha256 of csrc/ recorded next to the numbers), otherwise null
+    traffic, traffic_note = None, "no ncu --set full capture of this kernel for the current sources"
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(opts.config, {}).get(dominant)
+        tj = json.load(open(tpath))
+        if tj.get("csrc_sha256") == csrc_sha256():
+            traffic = tj.get(opts.config, {}).get(dominant)
+            traffic_note = f"dram__bytes_read.sum + dram__bytes_write.sum per launch, {tj.get('source', 'profiles/')}"
+        else:
+            traffic_note = "profiles/traffic.json was captured from other kernel sources (csrc sha256 differs): not quoted"
     roofline = {"kernel": "k_" + dominant, "bound": "hbm", "achieved": d["GBps"], "peak": peak, "unit": "GB/s", "frac": d["frac"],
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": d["bytes"], "us_per_launch": d["us"],
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": d["bytes"], "us_per_launch": d["us"],
+                "selection": "largest (mean launch duration x launches per update) among the hand-written kernels",
+                "us_per_step": round(step_kernel_us[dominant], 2),
+                "longest_single_launch": {"kernel": "k_" + longest, "us": kernels[longest]["us"], "frac": kernels[longest]["frac"]},
                 "timing": "CUDA events around each launch on its stream, eager (non-graph) replay of the same step",
                 "kernels": kernels,
                 "all_kernel_us": {k: round(v[1], 2) for k, v in kt.result.items()},
@@ -420,18 +492,20 @@ def ours(opts, cfg, rank, world, local):
             "config": workload_config(opts.config, cfg, world),
             "e2e": {"value": e2e_value, "unit": "updates/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": REPLAY_FREQUENCY * 84 * 84 * 4, "d2h_bytes_per_step": B * 4,
-                    "what": f"per step: {REPLAY_FREQUENCY} x mem.append(frame from pinned host memory) + dqn.reset_noise() + dqn.learn(mem) + "
-                            "per-sample loss copied to pinned host memory and read by the host one step behind the GPU (double buffer)"},
+                    "what": f"per step: {REPLAY_FREQUENCY} x mem.append(host frame) -- staged in the replay's pinned ring and written by one rb_append_batch "
+                            "launch that reads them in place over PCIe -- + dqn.reset_noise() + dqn.learn(mem) + per-sample loss copied to pinned host "
+                            "memory and read by the host one step behind the GPU (double buffer)"},
             # our kernels launched in the timed `value` region, per step: 2 k_noise_factors, k_tree_sample, k_gather,
             # 2 x (k_head_fc<.,1> + k_head_fc<.,2>), k_c51_dueling, k_head_wgrad2, k_head_dh, k_head_bwd1, 3 k_bias_grad,
             # k_sqnorm, k_clip_adam, k_tree_update_warp = 18 (the remaining ~19 graph nodes per step are cuDNN / ATen)
-            "gpu_launches": K * sum(launches_per_step.values()),
+            "gpu_launches": int(round(K * sum(launches_per_step.values()))),
             "clocks": clocks, "roofline": roofline}
     if world == 1 and not opts.no_cpu_baseline:
-        ups, dt, threads, n_cpu = run_cpu_port(cfg, opts.cpu_updates, 3, with_appends=True, budget_s=25)
-        line["cpu_baseline"] = {"value": ups, "unit": "updates/s", "cores": threads, "kind": "port",
-                                "sample": f"{n_cpu} updates of the same workload (each preceded by {REPLAY_FREQUENCY} appends) after 3 warm-up "
-                                          f"updates, {dt:.1f} s; oracle port: replay in C, nets in torch-CPU"}
+        del agent, mem, tr                                  # give the 7 GB of HBM back before the reference's GPU leg
+        torch.cuda.empty_cache()
+        ups, dt, threads, n_cpu, kind, sample, extra = cpu_arm(cfg, opts.cpu_updates, 3, budget_s=25, also_gpu=dev)
+        line["cpu_baseline"] = {"value": ups, "unit": "updates/s", "cores": threads, "kind": kind, "sample": sample}
+        line.update(extra)
     emit(line)
 
 
