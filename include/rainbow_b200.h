@@ -30,7 +30,8 @@
  *   action       int32[size]
  *   reward       float32[size]
  *   nonterminal  uint8[size]
- *   ring_state   int64[4]  {head (next write slot), full (0/1), t_episode, appended_total}
+ *   ring_state   int64[5]  {head (next write slot), full (0/1), t_episode, appended_total, launch ticket of
+ *                          rb_append_batch (zero between launches)}
  *   running_max  float32[1] largest exponentiated priority seen (memory.py:20,48)
  *   rng_counter  uint64[1]  Philox draw counter, advanced by the kernels themselves
  *                           (so a replayed CUDA graph draws fresh numbers)
@@ -72,7 +73,7 @@ enum {
   RB_K_TREE_UPDATE = 0, RB_K_TREE_FIND, RB_K_TREE_SAMPLE, RB_K_GATHER, RB_K_ITER_STATES, RB_K_APPEND, RB_K_C51,
   RB_K_NOISY_RESAMPLE, RB_K_NOISY_COMPOSE, RB_K_SQNORM, RB_K_CLIP_ADAM, RB_K_HEAD_FC1, RB_K_HEAD_FC2, RB_K_HEAD_LOGITS,
   RB_K_HEAD_WGRAD2, RB_K_HEAD_DH, RB_K_HEAD_BWD1, RB_K_NOISE_FACTORS, RB_K_C51_DUELING, RB_K_BIAS_GRAD, RB_K_Q_VALUES,
-  RB_KERNEL_COUNT
+  RB_K_HEAD_REDUCE1, RB_KERNEL_COUNT
 };
 
 int rb_abi_version(void);
@@ -201,16 +202,20 @@ typedef struct rb_head_grads {   /* gradients are OVERWRITTEN (not accumulated) 
 } rb_head_grads;
 
 /* split-K factors used by the head kernels: scratch part1 is float32[s1][M][2*hidden], part2 float32[s2][M][atoms*(1+actions)];
- * tickets is int32[rb_head_ticket_count()], zero-initialised ONCE by the caller (the kernels leave it zeroed). */
+ * tickets is int32[rb_head_ticket_count()], zero-initialised ONCE by the caller (the kernels leave it zeroed).
+ * s1 is the larger of the two layer-1 implementations' factors (tensor-core kernel, csrc/rb_head_tc.cu; FFMA kernel). */
 int rb_head_splits(int conv_features, int hidden, int* s1, int* s2);
 int rb_head_ticket_count(void);
-/* timing probes only: bit 0 skips the layer-1 launch of rb_head_forward, bit 1 the layer-2 launch (0 = normal) */
+/* probes / tests only: bit 0 skips the layer-1 launch of rb_head_forward, bit 1 the layer-2 launch, bit 2 forces the FFMA
+ * layer-1 kernel instead of the tensor-core one (0 = normal) */
 int rb_head_debug(int flags);
 
 /* Forward over M = m_lo + m_hi rows (x_lo: [m_lo][conv_features], x_hi: [m_hi][conv_features] or NULL).
  * Outputs: h[M][2*hidden] (post-ReLU hidden activations, value stream in columns [0,hidden), advantage stream in
- * [hidden,2*hidden)) and z[M][atoms*(1+actions)] = (z_value | z_advantage), biases included.  Two launches; the
- * split-K partials are reduced inside the kernels (last-arriving CTA, fixed order: deterministic). */
+ * [hidden,2*hidden)) and z[M][atoms*(1+actions)] = (z_value | z_advantage), biases included.
+ * Layer 1 runs on the tensor cores (TMA + tcgen05.mma, error-compensated TF32 = fp32-equivalent results; csrc/rb_head_tc.cu)
+ * followed by a fixed-order split-K reduction kernel; shapes that kernel does not cover (m_hi > 0 with m_lo % 8 != 0) and
+ * RB_HEAD_TC=0 in the environment use the FFMA kernel whose last-arriving CTA reduces the partials.  Deterministic. */
 int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const float* x_hi, int m_hi, float* part1, float* part2,
                     int32_t* tickets, float* h, float* z, rb_stream_t stream);
 

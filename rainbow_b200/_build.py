@@ -5,7 +5,7 @@ import subprocess
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
-SRCS = [os.path.join(PKG, "csrc", f) for f in ("rb_kernels.cu", "rb_head.cu", "rb_peer.cu")]
+SRCS = [os.path.join(PKG, "csrc", f) for f in ("rb_kernels.cu", "rb_head.cu", "rb_head_tc.cu", "rb_peer.cu")]
 DEPS = SRCS + [os.path.join(PKG, "csrc", "rb_internal.cuh")]
 HDR = os.path.join(ROOT, "include", "rainbow_b200.h")
 SO = os.path.join(PKG, "librainbow_b200.so")

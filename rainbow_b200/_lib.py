@@ -116,7 +116,7 @@ def stream():
 
 KERNEL_IDS = ["tree_update", "tree_find", "tree_sample", "gather", "iter_states", "append", "c51", "noisy_resample",
               "noisy_compose", "sqnorm", "clip_adam", "head_fc1", "head_fc2", "head_logits", "head_wgrad2", "head_dh",
-              "head_bwd1", "noise_factors", "c51_dueling", "bias_grad", "q_values"]  # order of the enum in include/rainbow_b200.h
+              "head_bwd1", "noise_factors", "c51_dueling", "bias_grad", "q_values", "head_reduce1"]  # order of the enum in include/rainbow_b200.h
 
 
 class KernelTimer:

@@ -787,12 +787,15 @@ int rb_head_splits(int conv_features, int hidden, int* s1, int* s2) {
   if (!s1 || !s2 || conv_features <= 0 || hidden <= 0) return rbi::fail(RB_ERR_INVAL, "rb_head_splits: bad argument");
   int a, b;
   head_splits(conv_features, hidden, s1, s2, &a, &b);
+  int s_tc, per;
+  rbi::head_fc1_tc_splits(conv_features, hidden, &s_tc, &per);   // part1 must hold whichever layer-1 kernel runs
+  if (s_tc > *s1) *s1 = s_tc;
   return RB_OK;
 }
 
 int rb_head_ticket_count(void) { return 4096; }
 
-static int g_head_debug = 0;   // bit 0: skip the layer-1 launch, bit 1: skip the layer-2 launch (timing probes only)
+static int g_head_debug = 0;   // bit 0: skip the layer-1 launch, bit 1: skip the layer-2 launch (timing probes only); bit 2: FFMA layer 1
 int rb_head_debug(int flags) {
   g_head_debug = flags;
   return RB_OK;
@@ -821,10 +824,15 @@ int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const 
   if (rc == RB_OK) rc = rbi::ensure_dynamic_smem(k_head_fc<32, 2>, smem32, "rb_head_forward");
   if (rc != RB_OK) return rc;
   if (!(g_head_debug & 1)) {
-    dim3 grid(tiles1, s1, mt);
-    rbi::ProfScope prof_(RB_K_HEAD_FC1, st);
-    if (MT == 64) k_head_fc<64, 1><<<grid, FC_T, smem64, st>>>(d, x_lo, m_lo, x_hi, M, part1, h, tickets, ks1);
-    else k_head_fc<32, 1><<<grid, FC_T, smem32, st>>>(d, x_lo, m_lo, x_hi, M, part1, h, tickets, ks1);
+    if (!(g_head_debug & 4) && rbi::head_fc1_tc_ok(d.K1, d.H, m_lo, m_hi)) {   // tensor cores: TMA + tcgen05.mma (3xTF32), then the fixed-order reduction
+      rc = rbi::head_fc1_tc(d.w1_mu, d.w1_sig, d.b1_mu, d.b1_sig, d.ei1, d.eo1, d.K1, d.H, x_lo, m_lo, x_hi, m_hi, part1, h, st);
+      if (rc != RB_OK) return rc;
+    } else {
+      dim3 grid(tiles1, s1, mt);
+      rbi::ProfScope prof_(RB_K_HEAD_FC1, st);
+      if (MT == 64) k_head_fc<64, 1><<<grid, FC_T, smem64, st>>>(d, x_lo, m_lo, x_hi, M, part1, h, tickets, ks1);
+      else k_head_fc<32, 1><<<grid, FC_T, smem32, st>>>(d, x_lo, m_lo, x_hi, M, part1, h, tickets, ks1);
+    }
   }
   rc = rbi::check_launch("rb_head_forward(fc1)");
   if (rc != RB_OK) return rc;

@@ -99,6 +99,13 @@ struct ProfScope {
   }
 };
 
+// ---- tensor-core layer 1 of the fused head (rb_head_tc.cu), called from rb_head_forward -----------------------------
+void head_fc1_tc_splits(int K1, int H, int* S, int* kt_per);
+bool head_fc1_tc_ok(int K1, int H, int m_lo, int m_hi);
+int head_fc1_tc(const float* const* w_mu, const float* const* w_sig, const float* const* b_mu, const float* const* b_sig,
+                const float* const* ei, const float* const* eo, int K1, int H, const float* x_lo, int m_lo, const float* x_hi,
+                int m_hi, float* part, float* h, cudaStream_t st);
+
 // ---- Philox4x32-10 counter-based RNG (Salmon et al. 2011) -------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;

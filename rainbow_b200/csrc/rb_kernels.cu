@@ -543,13 +543,25 @@ k_append(float* tree, int64_t tree_start, int64_t size, uint8_t* __restrict__ fr
   // frame: f32 * 255 then truncating cast (memory.py:106); 4 pixels per thread-iteration
   uint32_t* dst = reinterpret_cast<uint32_t*>(frames + (size_t)head * RB_FRAME_BYTES);
   const float4* src = reinterpret_cast<const float4*>(state_last);
-  for (int v = tid; v < RB_FRAME_BYTES / 4; v += APPEND_THREADS) {
-    float4 x = __ldg(src + v);
-    uint32_t a = (uint32_t)(uint8_t)(int)__fmul_rn(x.x, 255.0f);
-    uint32_t b = (uint32_t)(uint8_t)(int)__fmul_rn(x.y, 255.0f);
-    uint32_t c = (uint32_t)(uint8_t)(int)__fmul_rn(x.z, 255.0f);
-    uint32_t d = (uint32_t)(uint8_t)(int)__fmul_rn(x.w, 255.0f);
-    dst[v] = a | (b << 8) | (c << 16) | (d << 24);
+  {  // all of a thread's loads in flight at once: the frame may sit in pinned host memory (a PCIe round trip per load)
+    constexpr int PER = (RB_FRAME_BYTES / 4 + APPEND_THREADS - 1) / APPEND_THREADS;   // 7
+    float4 x[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int v = tid + u * APPEND_THREADS;
+      x[u] = (v < RB_FRAME_BYTES / 4) ? src[v] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int v = tid + u * APPEND_THREADS;
+      if (v < RB_FRAME_BYTES / 4) {
+        uint32_t a = (uint32_t)(uint8_t)(int)__fmul_rn(x[u].x, 255.0f);
+        uint32_t b = (uint32_t)(uint8_t)(int)__fmul_rn(x[u].y, 255.0f);
+        uint32_t c = (uint32_t)(uint8_t)(int)__fmul_rn(x[u].z, 255.0f);
+        uint32_t d = (uint32_t)(uint8_t)(int)__fmul_rn(x[u].w, 255.0f);
+        dst[v] = a | (b << 8) | (c << 16) | (d << 24);
+      }
+    }
   }
   if (tid < 32) {
     // warp 0: the walk.  All siblings along the path are independent of the new value, so lane j
@@ -611,25 +623,40 @@ __global__ void __launch_bounds__(APPEND_THREADS)
 k_append_batch(float* tree, int64_t tree_start, int64_t size, uint8_t* __restrict__ frames, int32_t* timestep,
                int32_t* action, float* reward, uint8_t* nonterminal, int64_t* ring_state, const float* running_max,
                const __grid_constant__ AppendBatch ab) {
+  // grid = k CTAs: CTA j quantises frame j (all of a thread's 16-byte loads in flight at once -- the frames may sit in
+  // pinned host memory, where every dependent load is a PCIe round trip); warp 0 of CTA 0 also writes the k records and
+  // walks the tree.  ring_state is read by every CTA when it starts and advanced by the LAST CTA to finish (ticket in
+  // ring_state[4]), so no CTA can see the new head.
   const int tid = threadIdx.x;
+  const int j = blockIdx.x;
   const int64_t head = ring_state[0];
   const int64_t t_ep0 = ring_state[2];
   const int k = ab.k;
-  for (int j = 0; j < k; ++j) {  // frames: f32 * 255 then truncating cast (memory.py:106)
+  {  // frame j: f32 * 255 then truncating cast (memory.py:106)
     int64_t slot = head + j;
     if (slot >= size) slot -= size;
     uint32_t* dst = reinterpret_cast<uint32_t*>(frames + (size_t)slot * RB_FRAME_BYTES);
     const float4* src = reinterpret_cast<const float4*>(ab.frame[j]);
-    for (int v = tid; v < RB_FRAME_BYTES / 4; v += APPEND_THREADS) {
-      const float4 x = src[v];
-      const uint32_t a = (uint32_t)(uint8_t)(int)__fmul_rn(x.x, 255.0f);
-      const uint32_t b = (uint32_t)(uint8_t)(int)__fmul_rn(x.y, 255.0f);
-      const uint32_t c = (uint32_t)(uint8_t)(int)__fmul_rn(x.z, 255.0f);
-      const uint32_t d = (uint32_t)(uint8_t)(int)__fmul_rn(x.w, 255.0f);
-      dst[v] = a | (b << 8) | (c << 16) | (d << 24);
+    constexpr int PER = (RB_FRAME_BYTES / 4 + APPEND_THREADS - 1) / APPEND_THREADS;   // 7
+    float4 x[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int v = tid + u * APPEND_THREADS;
+      x[u] = (v < RB_FRAME_BYTES / 4) ? src[v] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int v = tid + u * APPEND_THREADS;
+      if (v < RB_FRAME_BYTES / 4) {
+        const uint32_t a = (uint32_t)(uint8_t)(int)__fmul_rn(x[u].x, 255.0f);
+        const uint32_t b = (uint32_t)(uint8_t)(int)__fmul_rn(x[u].y, 255.0f);
+        const uint32_t c = (uint32_t)(uint8_t)(int)__fmul_rn(x[u].z, 255.0f);
+        const uint32_t d = (uint32_t)(uint8_t)(int)__fmul_rn(x[u].w, 255.0f);
+        dst[v] = a | (b << 8) | (c << 16) | (d << 24);
+      }
     }
   }
-  if (tid < 32) {
+  if (j == 0 && tid < 32) {
     const unsigned full = 0xffffffffu;
     const int lane = tid;
     const int L = tree_depth(tree_start);
@@ -674,18 +701,23 @@ k_append_batch(float* tree, int64_t tree_start, int64_t size, uint8_t* __restric
   }
   __syncthreads();
   if (tid == 0) {
-    int64_t nh = head + k;
-    bool wrapped = false;
-    if (nh >= size) {
-      nh -= size;
-      wrapped = true;
+    __threadfence();
+    unsigned long long* ticket = reinterpret_cast<unsigned long long*>(ring_state + 4);
+    if (atomicAdd(ticket, 1ull) == (unsigned long long)(k - 1)) {   // last CTA: everybody has read the old head
+      *ticket = 0ull;
+      int64_t nh = head + k;
+      bool wrapped = false;
+      if (nh >= size) {
+        nh -= size;
+        wrapped = true;
+      }
+      int64_t t = t_ep0;
+      for (int i = 0; i < k; ++i) t = ab.terminal[i] ? 0 : t + 1;
+      ring_state[0] = nh;
+      if (wrapped) ring_state[1] = 1;
+      ring_state[2] = t;
+      ring_state[3] = ring_state[3] + k;
     }
-    int64_t t = t_ep0;
-    for (int i = 0; i < k; ++i) t = ab.terminal[i] ? 0 : t + 1;
-    ring_state[0] = nh;
-    if (wrapped) ring_state[1] = 1;
-    ring_state[2] = t;
-    ring_state[3] = ring_state[3] + k;
   }
 }
 
@@ -1431,7 +1463,7 @@ int rb_append_batch(float* tree, int64_t tree_start, int64_t size, uint8_t* fram
     ab.terminal[j] = terminals[j] ? 1 : 0;
   }
   { ProfScope prof_(RB_K_APPEND, (cudaStream_t)stream);
-    k_append_batch<<<1, APPEND_THREADS, 0, (cudaStream_t)stream>>>(tree, tree_start, size, frames, timestep, action, reward,
+    k_append_batch<<<k, APPEND_THREADS, 0, (cudaStream_t)stream>>>(tree, tree_start, size, frames, timestep, action, reward,
                                                                    nonterminal, ring_state, running_max, ab); }
   return check_launch("rb_append_batch");
 }

@@ -69,7 +69,7 @@ class SegmentTree:
         self.action = torch.zeros(size, dtype=torch.int32, device=self.device)
         self.reward = torch.zeros(size, dtype=torch.float32, device=self.device)
         self.nonterminal = torch.zeros(size, dtype=torch.uint8, device=self.device)
-        self.ring_state = torch.zeros(4, dtype=torch.int64, device=self.device)  # head, full, t_episode, appended
+        self.ring_state = torch.zeros(5, dtype=torch.int64, device=self.device)  # head, full, t_episode, appended, ticket
         self.running_max = torch.ones(1, dtype=torch.float32, device=self.device)  # memory.py:20
         self._status = torch.zeros(4, dtype=torch.int32, device=self.device)
         self._lib = _lib.load()
@@ -187,7 +187,7 @@ class SegmentTree:
             self.index = int(index)
         if full is not None:
             self.full = bool(full)
-        self.ring_state.copy_(torch.tensor([self.index, int(self.full), int(t_episode), 0], dtype=torch.int64))
+        self.ring_state.copy_(torch.tensor([self.index, int(self.full), int(t_episode), 0, 0], dtype=torch.int64))
         if max_value is not None:
             self.running_max.fill_(float(max_value))
 

@@ -530,6 +530,43 @@ def test_fused_head_forward(arch, hidden, actions, rows):
     np.testing.assert_allclose(cpu(q_f), cpu(q_l), rtol=1e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize("arch,hidden,actions", [("canonical", 512, 6), ("data-efficient", 256, 6), ("data-efficient", 64, 3)])
+@pytest.mark.parametrize("m_lo,m_hi", [(32, 32), (32, 0), (16, 16), (8, 0), (1, 0), (40, 60), (20, 0)])
+def test_fused_head_layer1_tensor_core(arch, hidden, actions, m_lo, m_hi):
+    """Layer 1 on the tensor cores (csrc/rb_head_tc.cu: TMA + tcgen05.mma, error-compensated TF32) against the composed-weight
+    fp32 library GEMM (model.py:42-44) and against the FFMA kernel: fp32-equivalent results (<= 2e-5 of the tensor's scale,
+    the same bound the FFMA kernel is held to; observed ~1e-6), in training and eval mode, ragged row counts included."""
+    import torch.nn.functional as F
+    from rainbow_b200 import _lib
+    L = _lib.load()
+    net = _head_net(arch, hidden, actions)
+    torch.manual_seed(3)
+    x_lo = torch.randn(m_lo, net.conv_output_size, device=DEV).relu()
+    x_hi = torch.randn(m_hi, net.conv_output_size, device=DEV).relu() if m_hi else None
+    feats = x_lo if x_hi is None else torch.cat([x_lo, x_hi])
+    with torch.no_grad():
+        for mode in ("train", "eval"):
+            getattr(net, mode)()
+            h_ref = torch.cat([F.relu(net.fc_h_v(feats)), F.relu(net.fc_h_a(feats))], 1) if mode == "eval" else None
+            if mode == "train":
+                net.materialise_noise()
+                h_ref = torch.cat([F.relu(net.fc_h_v(feats)), F.relu(net.fc_h_a(feats))], 1)
+            v, a = _library_head(net, feats)
+            try:
+                L.rb_head_debug(4)                                   # FFMA layer 1
+                z_ff, h_ff, _ = net.head().forward(x_lo, x_hi)
+                z_ff, h_ff = z_ff.clone(), h_ff.clone()
+            finally:
+                L.rb_head_debug(0)
+            z, h, _ = net.head().forward(x_lo, x_hi)                 # tensor-core layer 1 (default)
+            np.testing.assert_allclose(cpu(h), cpu(h_ref), rtol=1e-4, atol=2e-5)
+            np.testing.assert_allclose(cpu(h), cpu(h_ff), rtol=1e-4, atol=2e-5)
+            np.testing.assert_allclose(cpu(z), cpu(torch.cat([v, a], 1)), rtol=1e-4, atol=2e-5)
+            z2, h2, _ = net.head().forward(x_lo, x_hi)               # deterministic: bit-identical on a second launch
+            assert torch.equal(h2, h) and torch.equal(z2, z)
+    net.train()
+
+
 def test_noise_factors_plus_outer_equals_resample():
     from rainbow_b200.model import resample_noise
     net = _head_net()
