@@ -559,6 +559,7 @@ def test_fused_head_layer1_tensor_core(arch, hidden, actions, m_lo, m_hi):
             finally:
                 L.rb_head_debug(0)
             z, h, _ = net.head().forward(x_lo, x_hi)                 # tensor-core layer 1 (default)
+            z, h = z.clone(), h.clone()
             np.testing.assert_allclose(cpu(h), cpu(h_ref), rtol=1e-4, atol=2e-5)
             np.testing.assert_allclose(cpu(h), cpu(h_ff), rtol=1e-4, atol=2e-5)
             np.testing.assert_allclose(cpu(z), cpu(torch.cat([v, a], 1)), rtol=1e-4, atol=2e-5)
