@@ -223,7 +223,8 @@ int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const 
 int rb_head_logits(const float* z, int M, int actions, int atoms, float* q, rb_stream_t stream);
 
 /* Backward for B <= 32 rows: given dz[B][atoms*(1+actions)] (value block first), x[B][conv_features] and h[B][2*hidden]
- * writes all 16 parameter gradients through `g` and dx[B][conv_features].  dh_scratch: float32[B][2*hidden].
+ * writes all 16 parameter gradients through `g` and dx[B][conv_features].  dh_scratch: float32[(B + 32) * 2*hidden]
+ * (dh [B][2*hidden], then its transpose [2*hidden][32] for the layer-1 kernel).
  * relu_mask_x != 0 additionally zeroes dx where x <= 0, i.e. folds in the backward of the ReLU that produced the conv
  * features (model.py:59), so dx is the gradient w.r.t. the last conv layer's pre-activation.
  * `parts` selects which of the three launches to enqueue (so a caller can put the independent layer-2 weight

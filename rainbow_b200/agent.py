@@ -370,7 +370,7 @@ class Agent:
                     after_loss(loss)
                     wb_done = torch.cuda.Event()
                     wb_done.record(s_ns)
-            dh = torch.empty((B, 2 * on.hidden_size), dtype=torch.float32, device=self.device)
+            dh = torch.empty((B + 32, 2 * on.hidden_size), dtype=torch.float32, device=self.device)   # dh, then its transpose
             dx = torch.empty_like(xs_d)
             if manual:
                 # dx comes back already masked by the last conv layer's ReLU; conv gradients are overwritten.

@@ -332,6 +332,97 @@ k_head_fc(const __grid_constant__ HeadDesc d, const float* __restrict__ x_lo, in
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Layer 2 forward in ONE pass (no split-K, no tickets): z[m][col(s) + n] = sum_k h[m][s*H + k] * W2_s[n][k] + b2_s[n].
+// The layer is tiny (357 x 512 weights per stream pair, 11.7 MFLOP at 64 rows) and purely latency bound, so the kernel is
+// organised around the number of dependent memory round trips: grid = one CTA per group of F2_ROWS weight rows (90 CTAs for
+// 51 atoms x (1 + 6 actions)) x 64-row batch tiles; the CTA's h slab [rows][H] arrives as one 1-D TMA bulk copy per batch
+// row (cp.async.bulk + mbarrier: a single memory latency for 128 KB) while all threads compose the CTA's F2_ROWS noisy weight
+// rows; thread (m, n) then runs one H-long dot product from shared memory (row stride H + 4 floats: conflict-free float4).
+// ------------------------------------------------------------------------------------------------
+constexpr int F2_ROWS = 4;
+constexpr int F2_T = 256;
+constexpr int F2_MT = F2_T / F2_ROWS;   // 64 batch rows per CTA
+
+__device__ __forceinline__ uint32_t f2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(F2_T)
+k_head_fc2(const __grid_constant__ HeadDesc d, const float* __restrict__ h, int M, float* __restrict__ z) {
+  extern __shared__ __align__(16) float f2_smem[];
+  const int H = d.H, LD = H + 4;
+  float* hs = f2_smem;                          // [F2_MT][LD]
+  float* ws = f2_smem + (size_t)F2_MT * LD;     // [F2_ROWS][LD]
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
+  const int groups0 = (d.Z + F2_ROWS - 1) / F2_ROWS;
+  const int s = ((int)blockIdx.x < groups0) ? 0 : 1;
+  const int r0 = (s == 0 ? (int)blockIdx.x : (int)blockIdx.x - groups0) * F2_ROWS;
+  const int Ns = n2_of(d, s), colbase = col2_of(d, s), ncols = d.Z + d.A * d.Z;
+  const int m0 = blockIdx.y * F2_MT, mrows = min(F2_MT, M - m0);
+  const uint32_t bar_a = f2_smem_u32(&bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {   // the whole activation slab in flight at once
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)(mrows * H * 4)) : "memory");
+    for (int r = 0; r < mrows; ++r)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(f2_smem_u32(hs + (size_t)r * LD)), "l"(h + (size_t)(m0 + r) * (2 * H) + s * H), "r"((uint32_t)(H * 4)), "r"(bar_a)
+                   : "memory");
+  }
+  {  // W2 rows of this CTA, composed: W = mu + sigma * (eps_out[n] * eps_in[k])   (model.py:39,43)
+    const float* __restrict__ mu = d.w2_mu[s];
+    const float* __restrict__ sg = d.w2_sig[s];
+    const float* ei = d.ei2[s];
+    const float* eo = d.eo2[s];
+    const int per_row = H >> 2;
+    for (int idx = tid; idx < F2_ROWS * per_row; idx += F2_T) {
+      const int n = idx / per_row, k4 = (idx - n * per_row) << 2, row = r0 + n;
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < Ns) {
+        w = __ldg(reinterpret_cast<const float4*>(mu + (size_t)row * H + k4));
+        if (ei) {
+          const float4 s4 = __ldg(reinterpret_cast<const float4*>(sg + (size_t)row * H + k4));
+          const float4 e4 = __ldg(reinterpret_cast<const float4*>(ei + k4));
+          const float e = __ldg(eo + row);
+          w.x = fmaf(s4.x, e * e4.x, w.x); w.y = fmaf(s4.y, e * e4.y, w.y);
+          w.z = fmaf(s4.z, e * e4.z, w.z); w.w = fmaf(s4.w, e * e4.w, w.w);
+        }
+      }
+      *reinterpret_cast<float4*>(ws + (size_t)n * LD + k4) = w;
+    }
+  }
+  __syncthreads();
+  {  // every thread waits for the bulk copies (phase 0 of the barrier)
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "F2WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra F2DONE_%=;\n\t"
+        "bra F2WAIT_%=;\n\t"
+        "F2DONE_%=:\n\t"
+        "}\n" ::"r"(bar_a) : "memory");
+  }
+  const int m = tid / F2_ROWS, n = tid % F2_ROWS, row = r0 + n;
+  if (m < mrows && row < Ns) {
+    const float* hr = hs + (size_t)m * LD;
+    const float* wr = ws + (size_t)n * LD;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four independent chains
+#pragma unroll 8
+    for (int k = 0; k < H; k += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(hr + k);
+      const float4 b = *reinterpret_cast<const float4*>(wr + k);
+      a0 = fmaf(a.x, b.x, a0); a1 = fmaf(a.y, b.y, a1); a2 = fmaf(a.z, b.z, a2); a3 = fmaf(a.w, b.w, a3);
+    }
+    float bv = __ldg(d.b2_mu[s] + row);
+    if (d.eo2[s]) bv = fmaf(__ldg(d.b2_sig[s] + row), __ldg(d.eo2[s] + row), bv);
+    z[(size_t)(m0 + m) * ncols + colbase + row] = ((a0 + a1) + (a2 + a3)) + bv;
+  }
+}
+
 // q[m][a][z] = zv[z] + za[a][z] - mean_a za[.][z]  (model.py:73-75) from the head output z[m][Z + A*Z].
 __global__ void __launch_bounds__(128)
 k_head_logits(int Z, int A, const float* __restrict__ z, float* __restrict__ q) {
@@ -430,7 +521,7 @@ constexpr int DH_SPLIT = 4;  // CTAs per cluster: the stream's rows of W2 are sp
 
 __global__ void __cluster_dims__(1, DH_SPLIT, 1) __launch_bounds__(HT)
 k_head_dh(const __grid_constant__ HeadDesc d, const float* __restrict__ dz, const float* __restrict__ h, int B,
-          float* __restrict__ dh, int rows_pad) {
+          float* __restrict__ dh, float* __restrict__ dhT, int rows_pad) {
   extern __shared__ __align__(16) float smem_dh[];
   float* Wm = smem_dh;                           // [rows_pad][DH_LD] raw mu, composed in place
   float* Wsg = Wm + (size_t)rows_pad * DH_LD;    // [rows_pad][DH_LD] raw sigma
@@ -520,13 +611,17 @@ k_head_dh(const __grid_constant__ HeadDesc d, const float* __restrict__ dz, cons
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int m = tm * 2 + i;
-      if (m >= B) continue;
-      const size_t off = (size_t)m * (2 * d.H) + s * d.H + k0 + tk * 4;
-      const float4 hv = __ldg(reinterpret_cast<const float4*>(h + off));
-      float4 o4;
-      o4.x = hv.x > 0.f ? acc[i][0] : 0.f; o4.y = hv.y > 0.f ? acc[i][1] : 0.f;
-      o4.z = hv.z > 0.f ? acc[i][2] : 0.f; o4.w = hv.w > 0.f ? acc[i][3] : 0.f;
-      *reinterpret_cast<float4*>(dh + off) = o4;
+      float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < B) {
+        const size_t off = (size_t)m * (2 * d.H) + s * d.H + k0 + tk * 4;
+        const float4 hv = __ldg(reinterpret_cast<const float4*>(h + off));
+        o4.x = hv.x > 0.f ? acc[i][0] : 0.f; o4.y = hv.y > 0.f ? acc[i][1] : 0.f;
+        o4.z = hv.z > 0.f ? acc[i][2] : 0.f; o4.w = hv.w > 0.f ? acc[i][3] : 0.f;
+        *reinterpret_cast<float4*>(dh + off) = o4;
+      }
+      // transposed copy [2H][32] (rows past B are zero) for the layer-1 kernel's input-gradient half
+      float* t = dhT + (size_t)(s * d.H + k0 + tk * 4) * 32 + m;
+      t[0] = o4.x; t[32] = o4.y; t[64] = o4.z; t[96] = o4.w;
     }
   }
   cluster.sync();  // remote shared memory must outlive the reads above
@@ -539,32 +634,57 @@ k_head_dh(const __grid_constant__ HeadDesc d, const float* __restrict__ dz, cons
 // grid = (K1/32, 2 streams x 2 halves of the stream's rows) launched as clusters of 4 CTAs along y: three CTAs
 // hand their dx partial to rank 0 through distributed shared memory (fixed rank order -> deterministic).
 // 256 threads: warps 0-3 compute the weight-gradient tile of the current 32-row chunk of W1 while warps
-// 4-7 accumulate the input gradient from the same staged tiles; all 8 warps prefetch the next chunk.
+// 4-7 accumulate the input gradient from the same staged tiles.  The chunks (raw mu / sigma rows, the dh chunk in both
+// orientations -- k_head_dh writes dh [m][2H] and its transpose dhT [2H][32], so nothing is transposed through shared
+// memory here) arrive through a 3-stage cp.async ring, two chunks ahead of the one being consumed: the eight dependent
+// memory latencies of the old single-stage register prefetch collapse into one plus streaming.
 // ------------------------------------------------------------------------------------------------
 constexpr int B1_K = 32;   // k columns per CTA
 constexpr int B1_O = 32;   // rows of W1 per chunk
 constexpr int B1_T = 256;  // threads
 
+constexpr int B1_STAGES = 3;                 // cp.async ring: two chunks in flight ahead of the one being consumed (3 CTAs per SM: one wave)
+constexpr int B1_LD = B1_K + 4;              // row stride of every staged tile (floats): 144 B, keeps 16-byte alignment
+constexpr int B1_STAGE = 4 * 32 * B1_LD;     // floats per stage: W mu (composed in place) | W sigma | dh [m][o] | dhT [o][m]
+
 __global__ void __cluster_dims__(1, 4, 1) __launch_bounds__(B1_T)
 k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrads g, const float* __restrict__ x,
-            const float* __restrict__ dh, int B, float* __restrict__ dx, int relu_mask_x) {
+            const float* __restrict__ dh, const float* __restrict__ dhT, int B, float* __restrict__ dx, int relu_mask_x) {
+  extern __shared__ __align__(16) float b1_ring[];     // [B1_STAGES][B1_STAGE]
   __shared__ __align__(16) float Xs[32][B1_K + 4];    // x slice [m][k]
-  __shared__ __align__(16) float Ds[32][B1_O + 4];    // dh chunk [m][o]
-  __shared__ __align__(16) float DsT[B1_O][32 + 4];   // dh chunk [o][m]
-  __shared__ __align__(16) float Ws[B1_O][B1_K + 4];  // composed W1 chunk [o][k]
   __shared__ __align__(16) float Red[32][B1_K + 4];   // dx partial handed over the cluster
-  __shared__ float Eo[B1_O];                          // eps_out of the chunk's rows
+  __shared__ float Eo[B1_STAGES][B1_O];               // eps_out of the staged chunks' rows
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x;
   const int role = tid >> 7, rt = tid & 127, tk = rt & 15, to = rt >> 4;  // micro tile: 4 rows (o or m) x 2 k
   // cluster of 4 CTAs along y: (stream, half of the stream's W1 rows); rank 0 sums the four dx partials
   const int s = blockIdx.y >> 1, half = blockIdx.y & 1, k0 = blockIdx.x * B1_K, K = d.K1, H = d.H;
-  const int o_begin = half * (H / 2), o_end = o_begin + H / 2;
+  const int o_begin = half * (H / 2), n_chunks = (H / 2) / B1_O;
   const float* __restrict__ mu = d.w1_mu[s];
   const float* __restrict__ sg = d.w1_sig[s];
   const float* ei = d.ei1[s];
   const float* eo = d.eo1[s];
+  const int st_r = tid >> 3, st_c = (tid & 7) * 4;   // staging coordinates: one 16-byte chunk of each of the four tiles
 
+  auto Wm = [&](int st) { return b1_ring + (size_t)st * B1_STAGE; };
+  auto Wsg = [&](int st) { return b1_ring + (size_t)st * B1_STAGE + 32 * B1_LD; };
+  auto Dm = [&](int st) { return b1_ring + (size_t)st * B1_STAGE + 2 * 32 * B1_LD; };   // dh chunk [m][o]
+  auto Dt = [&](int st) { return b1_ring + (size_t)st * B1_STAGE + 3 * 32 * B1_LD; };   // dh chunk [o][m]
+  auto issue = [&](int c) {   // chunk c of this CTA's rows -> stage c % B1_STAGES (always commits, possibly an empty group)
+    if (c < n_chunks) {
+      const int st = c % B1_STAGES, ob = o_begin + c * B1_O;
+      cp_async16_zfill(Wm(st) + st_r * B1_LD + st_c, mu + (size_t)(ob + st_r) * K + k0 + st_c, true);
+      if (ei) cp_async16_zfill(Wsg(st) + st_r * B1_LD + st_c, sg + (size_t)(ob + st_r) * K + k0 + st_c, true);
+      const bool row_ok = st_r < B;
+      cp_async16_zfill(Dm(st) + st_r * B1_LD + st_c, row_ok ? dh + (size_t)st_r * (2 * H) + s * H + ob + st_c : dh, row_ok);
+      cp_async16_zfill(Dt(st) + st_r * B1_LD + st_c, dhT + (size_t)(s * H + ob + st_r) * 32 + st_c, true);
+      if (st_c == 0) Eo[st][st_r] = eo ? __ldg(eo + ob + st_r) : 0.0f;
+    }
+    cp_async_commit();
+  };
+
+#pragma unroll
+  for (int c = 0; c < B1_STAGES - 1; ++c) issue(c);
   {  // x slice: 32 rows x 8 float4 = 256 float4, one per thread
     const int m = tid >> 3, kk = (tid & 7) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -572,8 +692,6 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
     *reinterpret_cast<float4*>(&Xs[m][kk]) = v;
   }
   const float ei0 = ei ? __ldg(ei + k0 + tk * 2) : 0.0f, ei1v = ei ? __ldg(ei + k0 + tk * 2 + 1) : 0.0f;
-  // staging coordinates of this thread (one float4 of mu, sigma, dh per chunk)
-  const int st_r = tid >> 3, st_c = (tid & 7) * 4;
   float4 e4s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ei) e4s = __ldg(reinterpret_cast<const float4*>(ei + k0 + st_c));
 
@@ -581,41 +699,29 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
 #pragma unroll
   for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0f;
 
-  float4 pmu, psg, pdh;
-  float peo = 0.0f;
-  auto prefetch = [&](int ob) {
-    pmu = __ldg(reinterpret_cast<const float4*>(mu + (size_t)(ob + st_r) * K + k0 + st_c));
-    psg = ei ? __ldg(reinterpret_cast<const float4*>(sg + (size_t)(ob + st_r) * K + k0 + st_c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    pdh = (st_r < B) ? __ldg(reinterpret_cast<const float4*>(dh + (size_t)st_r * (2 * H) + s * H + ob + st_c))
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
-    peo = eo ? __ldg(eo + ob + st_r) : 0.0f;
-  };
-  auto commit = [&]() {
-    float4 w = pmu;
-    if (ei) {
-      w.x = fmaf(psg.x, peo * e4s.x, w.x); w.y = fmaf(psg.y, peo * e4s.y, w.y);
-      w.z = fmaf(psg.z, peo * e4s.z, w.z); w.w = fmaf(psg.w, peo * e4s.w, w.w);
+  for (int c = 0; c < n_chunks; ++c) {
+    const int st = c % B1_STAGES, ob = o_begin + c * B1_O;
+    cp_async_wait<B1_STAGES - 2>();   // this thread's copies of chunk c have landed ...
+    __syncthreads();                  // ... and everybody else's; everybody is also done with chunk c - 1
+    issue(c + B1_STAGES - 1);         // overwrites the stage chunk c - 1 used
+    if (ei) {                         // W = mu + sigma * (eps_out[o] * eps_in[k]) in place   (model.py:39,43)
+      float4 w = *reinterpret_cast<const float4*>(Wm(st) + st_r * B1_LD + st_c);
+      const float4 sg4 = *reinterpret_cast<const float4*>(Wsg(st) + st_r * B1_LD + st_c);
+      const float e = Eo[st][st_r];
+      w.x = fmaf(sg4.x, e * e4s.x, w.x); w.y = fmaf(sg4.y, e * e4s.y, w.y);
+      w.z = fmaf(sg4.z, e * e4s.z, w.z); w.w = fmaf(sg4.w, e * e4s.w, w.w);
+      *reinterpret_cast<float4*>(Wm(st) + st_r * B1_LD + st_c) = w;
+      __syncthreads();
     }
-    *reinterpret_cast<float4*>(&Ws[st_r][st_c]) = w;
-    *reinterpret_cast<float4*>(&Ds[st_r][st_c]) = pdh;
-    DsT[st_c + 0][st_r] = pdh.x; DsT[st_c + 1][st_r] = pdh.y; DsT[st_c + 2][st_r] = pdh.z; DsT[st_c + 3][st_r] = pdh.w;
-    if (st_c == 0) Eo[st_r] = peo;
-  };
-
-  prefetch(o_begin);
-  commit();
-  __syncthreads();
-  for (int ob = o_begin; ob < o_end; ob += B1_O) {
-    const bool more = ob + B1_O < o_end;
-    if (more) prefetch(ob + B1_O);
     if (role == 0) {
       // ---- weight gradient tile [32 o][32 k]: reduction over the batch rows ----
+      const float* Ds = Dm(st);
       float ga[4][2];
 #pragma unroll
       for (int i = 0; i < 4; ++i) ga[i][0] = ga[i][1] = 0.0f;
 #pragma unroll 8
       for (int m = 0; m < 32; ++m) {
-        const float4 a = *reinterpret_cast<const float4*>(&Ds[m][to * 4]);
+        const float4 a = *reinterpret_cast<const float4*>(Ds + m * B1_LD + to * 4);
         const float2 b = *reinterpret_cast<const float2*>(&Xs[m][tk * 2]);
         ga[0][0] = fmaf(a.x, b.x, ga[0][0]); ga[0][1] = fmaf(a.x, b.y, ga[0][1]);
         ga[1][0] = fmaf(a.y, b.x, ga[1][0]); ga[1][1] = fmaf(a.y, b.y, ga[1][1]);
@@ -627,33 +733,31 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
         const int o = ob + to * 4 + i;
         const size_t off = (size_t)o * K + k0 + tk * 2;
         __stcs(reinterpret_cast<float2*>(g.w1_mu[s] + off), make_float2(ga[i][0], ga[i][1]));
-        const float e = Eo[to * 4 + i];
+        const float e = Eo[st][to * 4 + i];
         __stcs(reinterpret_cast<float2*>(g.w1_sig[s] + off), make_float2(ga[i][0] * (e * ei0), ga[i][1] * (e * ei1v)));
       }
       if (blockIdx.x == 0 && rt < B1_O) {  // bias gradients of this chunk's rows
         float bs = 0.0f;
-        for (int m = 0; m < 32; ++m) bs += Ds[m][rt];
+        for (int m = 0; m < 32; ++m) bs += Ds[m * B1_LD + rt];
         g.b1_mu[s][ob + rt] = bs;
-        g.b1_sig[s][ob + rt] = bs * Eo[rt];
+        g.b1_sig[s][ob + rt] = bs * Eo[st][rt];
       }
     } else {
       // ---- input gradient [32 m][32 k]: reduction over this chunk's rows of W1 ----
+      const float* DsT = Dt(st);
+      const float* Ws = Wm(st);
 #pragma unroll 8
       for (int oo = 0; oo < B1_O; ++oo) {
-        const float4 a = *reinterpret_cast<const float4*>(&DsT[oo][to * 4]);
-        const float2 b = *reinterpret_cast<const float2*>(&Ws[oo][tk * 2]);
+        const float4 a = *reinterpret_cast<const float4*>(DsT + oo * B1_LD + to * 4);
+        const float2 b = *reinterpret_cast<const float2*>(Ws + oo * B1_LD + tk * 2);
         acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
         acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
         acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]);
         acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]);
       }
     }
-    __syncthreads();
-    if (more) {
-      commit();
-      __syncthreads();
-    }
   }
+  cp_async_wait<0>();
   // ---- dx = sum of the four partials (fixed rank order), over distributed shared memory ----
   const unsigned rank = cluster.block_rank();
   if (rank != 0 && role == 1) {
@@ -795,7 +899,7 @@ int rb_head_splits(int conv_features, int hidden, int* s1, int* s2) {
 
 int rb_head_ticket_count(void) { return 4096; }
 
-static int g_head_debug = 0;   // bit 0: skip the layer-1 launch, bit 1: skip the layer-2 launch (timing probes only); bit 2: FFMA layer 1
+static int g_head_debug = 0;   // bit 0: skip the layer-1 launch, bit 1: skip the layer-2 launch (timing probes only); bit 2: FFMA layer 1; bit 3: split-K layer 2
 int rb_head_debug(int flags) {
   g_head_debug = flags;
   return RB_OK;
@@ -837,10 +941,18 @@ int rb_head_forward(const rb_head_params* p, const float* x_lo, int m_lo, const 
   rc = rbi::check_launch("rb_head_forward(fc1)");
   if (rc != RB_OK) return rc;
   if (!(g_head_debug & 2)) {
-    dim3 grid(tiles2, s2, mt);
+    const size_t smem_f2 = (size_t)(F2_MT + F2_ROWS) * (d.H + 4) * sizeof(float);
     rbi::ProfScope prof_(RB_K_HEAD_FC2, st);
-    if (MT == 64) k_head_fc<64, 2><<<grid, FC_T, smem64, st>>>(d, h, M, nullptr, M, part2, z, tickets + 2048, ks2);
-    else k_head_fc<32, 2><<<grid, FC_T, smem32, st>>>(d, h, M, nullptr, M, part2, z, tickets + 2048, ks2);
+    if (smem_f2 <= 200 * 1024 && d.H % 4 == 0 && !(g_head_debug & 8)) {   // single pass, no split-K (the usual shapes)
+      rc = rbi::ensure_dynamic_smem(k_head_fc2, smem_f2, "rb_head_forward(fc2)");
+      if (rc != RB_OK) return rc;
+      dim3 grid((d.Z + F2_ROWS - 1) / F2_ROWS + (d.A * d.Z + F2_ROWS - 1) / F2_ROWS, (M + F2_MT - 1) / F2_MT);
+      k_head_fc2<<<grid, F2_T, smem_f2, st>>>(d, h, M, z);
+    } else {
+      dim3 grid(tiles2, s2, mt);
+      if (MT == 64) k_head_fc<64, 2><<<grid, FC_T, smem64, st>>>(d, h, M, nullptr, M, part2, z, tickets + 2048, ks2);
+      else k_head_fc<32, 2><<<grid, FC_T, smem32, st>>>(d, h, M, nullptr, M, part2, z, tickets + 2048, ks2);
+    }
   }
   return rbi::check_launch("rb_head_forward(fc2)");
 }
@@ -888,14 +1000,17 @@ int rb_head_backward(const rb_head_params* p, const rb_head_grads* gr, const flo
     if (rc != RB_OK) return rc;
     dim3 grid(d.H / DH_K, 2 * DH_SPLIT);
     rbi::ProfScope prof_(RB_K_HEAD_DH, st);
-    k_head_dh<<<grid, HT, smem, st>>>(d, dz, h, B, dh_scratch, rows_pad);
+    k_head_dh<<<grid, HT, smem, st>>>(d, dz, h, B, dh_scratch, dh_scratch + (size_t)B * 2 * d.H, rows_pad);
   }
   rc = rbi::check_launch("rb_head_backward(dh)");
   if (rc != RB_OK) return rc;
   if (parts & RB_HEAD_BWD_LAYER1) {
     dim3 grid(d.K1 / B1_K, 4);
     rbi::ProfScope prof_(RB_K_HEAD_BWD1, st);
-    k_head_bwd1<<<grid, B1_T, 0, st>>>(d, g, x, dh_scratch, B, dx, relu_mask_x);
+    const size_t smem_b1 = (size_t)B1_STAGES * B1_STAGE * sizeof(float);
+    rc = rbi::ensure_dynamic_smem(k_head_bwd1, smem_b1, "rb_head_backward");
+    if (rc != RB_OK) return rc;
+    k_head_bwd1<<<grid, B1_T, smem_b1, st>>>(d, g, x, dh_scratch, dh_scratch + (size_t)B * 2 * d.H, B, dx, relu_mask_x);
   }
   return rbi::check_launch("rb_head_backward(bwd1)");
 }

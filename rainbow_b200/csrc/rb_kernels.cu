@@ -760,13 +760,38 @@ __device__ __forceinline__ void softmax_row(const float* row, int Z, int lane, f
   sum = warp_sum(sum);
 }
 
+// Expected value sum_z support_z * p_z of one logit row held in registers (x[r] = logit of atom lane + 32 r, -inf past Z),
+// p = e / sum(e): the numerator and sum(e) ride the same shuffle butterfly (two independent shuffles per step) and one
+// division finishes the row (agent.py:71-72).  All lanes return the value.
+template <int C51_R>
+__device__ __forceinline__ float c51_expected_value(const float (&x)[C51_R], const float (&sup)[C51_R], int Z, int lane) {
+  float mx = -CUDART_INF_F;
+#pragma unroll
+  for (int r = 0; r < C51_R; ++r) mx = fmaxf(mx, x[r]);
+  mx = warp_max(mx);
+  float se = 0.0f, sn = 0.0f;
+#pragma unroll
+  for (int r = 0; r < C51_R; ++r) {
+    const float ee = (lane + 32 * r < Z) ? expf(x[r] - mx) : 0.0f;
+    se = __fadd_rn(se, ee);
+    sn = __fadd_rn(sn, __fmul_rn(sup[r], ee));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    se = __fadd_rn(se, __shfl_xor_sync(0xffffffffu, se, o));
+    sn = __fadd_rn(sn, __shfl_xor_sync(0xffffffffu, sn, o));
+  }
+  return __fdiv_rn(sn, se);
+}
+
 // q_on_ns / q_tg_ns: A rows of Z (row stride Z); q_on_s_act: the row of the taken action.
+// best_known >= 0: a* was already determined by the caller (q_on_ns is then not read, q_tg_ns points at the row of a*).
 template <int C51_R>
 __device__ __forceinline__ void c51_core(C51Scratch& sc, int lane, int i, int B, int A, int Z, const float* q_on_ns,
                                          const float* q_tg_ns, const float* q_on_s_act, float ret, float nonterminal,
                                          float weight, const float* __restrict__ support, float vmin, float vmax,
                                          float delta_z, float gamma_n, float* __restrict__ loss, float* __restrict__ m_out,
-                                         int64_t* __restrict__ astar_out, float (&g)[C51_R]) {
+                                         int64_t* __restrict__ astar_out, float (&g)[C51_R], int best_known = -1) {
   float sup[C51_R];
 #pragma unroll
   for (int r = 0; r < C51_R; ++r) {
@@ -777,41 +802,28 @@ __device__ __forceinline__ void c51_core(C51Scratch& sc, int lane, int i, int B,
 
   // ---- agent.py:71-73: a* = argmax_a sum_z support_z * softmax(q_online(s'))[a,z] ----
   int best = 0;
-  float best_ev = -CUDART_INF_F;
-  for (int a = 0; a < A; ++a) {
-    // expected value sum_z support_z * p_z with p = e / sum(e): the numerator and sum(e) ride the same shuffle
-    // butterfly (two independent shuffles per step) and one division finishes the row
-    const float* row = q_on_ns + (size_t)a * Z;
-    mx = -CUDART_INF_F;
+  if (best_known >= 0) {
+    best = best_known;
+  } else {
+    float best_ev = -CUDART_INF_F;
+    for (int a = 0; a < A; ++a) {
+      const float* row = q_on_ns + (size_t)a * Z;
 #pragma unroll
-    for (int r = 0; r < C51_R; ++r) {
-      int z = lane + 32 * r;
-      x[r] = (z < Z) ? row[z] : -CUDART_INF_F;
-      mx = fmaxf(mx, x[r]);
-    }
-    mx = warp_max(mx);
-    float se = 0.0f, sn = 0.0f;
-#pragma unroll
-    for (int r = 0; r < C51_R; ++r) {
-      const float ee = (lane + 32 * r < Z) ? expf(x[r] - mx) : 0.0f;
-      se = __fadd_rn(se, ee);
-      sn = __fadd_rn(sn, __fmul_rn(sup[r], ee));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      se = __fadd_rn(se, __shfl_xor_sync(0xffffffffu, se, o));
-      sn = __fadd_rn(sn, __shfl_xor_sync(0xffffffffu, sn, o));
-    }
-    const float ev = __fdiv_rn(sn, se);
-    if (ev > best_ev) {  // first maximum wins, like torch.argmax
-      best_ev = ev;
-      best = a;
+      for (int r = 0; r < C51_R; ++r) {
+        int z = lane + 32 * r;
+        x[r] = (z < Z) ? row[z] : -CUDART_INF_F;
+      }
+      const float ev = c51_expected_value<C51_R>(x, sup, Z, lane);
+      if (ev > best_ev) {  // first maximum wins, like torch.argmax
+        best_ev = ev;
+        best = a;
+      }
     }
   }
   if (astar_out && lane == 0) astar_out[i] = best;
 
   // ---- agent.py:75-76: target distribution of the selected action ----
-  softmax_row(q_tg_ns + (size_t)best * Z, Z, lane, e, x, mx, sum);
+  softmax_row(q_tg_ns + (best_known >= 0 ? (size_t)0 : (size_t)best * Z), Z, lane, e, x, mx, sum);
 #pragma unroll
   for (int r = 0; r < C51_R; ++r) {
     int z = lane + 32 * r;
@@ -931,86 +943,125 @@ k_c51(const float* __restrict__ q_on_s, const float* __restrict__ q_on_ns, const
 }
 
 // Dueling entry point: fed by the fused heads' outputs z = (z_value | z_advantage) [rows][Z + A*Z]
-// (online net: 2B rows, s then s'; target net: B rows).  The CTA stages the z rows of its four samples in
-// shared memory with coalesced loads, each warp assembles its logit rows
-// q[a][z] = zv[z] + za[a][z] - mean_a za[.][z] (model.py:73-75) there, and the gradient is returned w.r.t.
-// the head outputs:  dzv[z] = g[z],  dza[a][z] = g[z] * ([a == act] - 1/A).
+// (online net: 2B rows, s then s'; target net: B rows).  ONE CTA PER SAMPLE, 8 warps: the kernel is pure dependent latency
+// (184 KB in, 46 KB out), so the serial chain per sample is cut instead of packing samples into few CTAs:
+//   phase 0  all threads stage the sample's three z rows in shared memory (every load in flight at once);
+//   phase 1  warp a computes the expected value of action a of the online net on s' (model.py:75 dueling combination on the
+//            fly, softmax, expectation) -- the A softmax rows of the double-DQN arg-max run side by side, not in sequence;
+//   phase 2  warp 0 takes the arg-max (first maximum wins), assembles the two logit rows still needed (target net at a*,
+//            online net at the taken action) and runs the projection / loss / gradient (c51_core, same arithmetic as the
+//            plain entry point);
+//   phase 3  all threads write dz:  dzv[z] = g[z],  dza[a][z] = g[z] * ([a == act] - 1/A).
+constexpr int C51D_T = 256;
+
 template <int C51_R>
-__global__ void __launch_bounds__(C51_WARPS * 32)
+__global__ void __launch_bounds__(C51D_T)
 k_c51_dueling(const float* __restrict__ z_on, const float* __restrict__ z_tg, const int64_t* __restrict__ actions,
               const float* __restrict__ returns, const float* __restrict__ nonterminals, const float* __restrict__ weights,
               const float* __restrict__ support, float vmin, float vmax, float delta_z, float gamma_n, int B, int A, int Z,
               float* __restrict__ loss, float* __restrict__ dz, float* __restrict__ m_out, int64_t* __restrict__ astar_out) {
   extern __shared__ __align__(16) float s_dyn[];
-  __shared__ C51Scratch s_sc[C51_WARPS];
+  __shared__ C51Scratch s_sc;
   const int N2 = Z + A * Z;
-  // layout: zs[C51_WARPS][3][N2] (online s, online s', target s'), then per warp q rows [2*A*Z + Z]
-  float* zs = s_dyn;
-  float* qs = s_dyn + (size_t)C51_WARPS * 3 * N2;
-  const int i0 = blockIdx.x * C51_WARPS;
+  float* zs = s_dyn;              // [3][N2]: online(s), online(s'), target(s')
+  float* q_t = zs + 3 * N2;       // [Z] target logits of a*
+  float* q_s = q_t + Z;           // [Z] online logits of the taken action
+  float* s_g = q_s + Z;           // [Z] gradient row
+  float* s_ev = s_g + Z;          // [A] expected values
+  const int i = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {
-    const int total = C51_WARPS * 3 * N2;
-    for (int base = threadIdx.x; base < total; base += blockDim.x * 8) {
+    const int total = 3 * N2;
+    const float* src[3] = {z_on + (size_t)i * N2, z_on + (size_t)(B + i) * N2, z_tg + (size_t)i * N2};
+    for (int base = tid; base < total; base += C51D_T * 8) {
       float v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {  // eight independent loads in flight per thread, then the stores
-        const int idx = base + u * blockDim.x;
+        const int idx = base + u * C51D_T;
         v[u] = 0.0f;
         if (idx < total) {
-          const int w = idx / (3 * N2), rem = idx - w * 3 * N2, t = rem / N2, c = rem - t * N2, i = i0 + w;
-          if (i < B) v[u] = (t == 0) ? __ldg(z_on + (size_t)i * N2 + c) : (t == 1) ? __ldg(z_on + (size_t)(B + i) * N2 + c) : __ldg(z_tg + (size_t)i * N2 + c);
+          const int t = idx / N2;
+          v[u] = __ldg(src[t] + (idx - t * N2));
         }
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int idx = base + u * blockDim.x;
+        const int idx = base + u * C51D_T;
         if (idx < total) zs[idx] = v[u];
       }
     }
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = i0 + warp;
-  if (i >= B) return;
-  const float* zw = zs + (size_t)warp * 3 * N2;
-  float* q_ns = qs + (size_t)warp * (2 * A * Z + Z);
-  float* q_t = q_ns + A * Z;
-  float* q_s = q_t + A * Z;
   const int act = (int)actions[i];
-  const float inv_a = 1.0f / (float)A;
-  for (int c = lane; c < Z; c += 32) {
-    {  // online(s): the taken action only
-      const float* r = zw;
-      float mean = 0.0f;
-      for (int a = 0; a < A; ++a) mean += r[Z + a * Z + c];
-      q_s[c] = r[c] + r[Z + act * Z + c] - mean / (float)A;
+  float sup[C51_R];
+#pragma unroll
+  for (int r = 0; r < C51_R; ++r) sup[r] = (lane + 32 * r < Z) ? __ldg(support + lane + 32 * r) : 0.0f;
+  {  // phase 1: expected value of every action of online(s'), one warp per action
+    const float* r1 = zs + N2;
+    float mean[C51_R];
+#pragma unroll
+    for (int r = 0; r < C51_R; ++r) {
+      const int c = lane + 32 * r;
+      float acc = 0.0f;
+      if (c < Z)
+        for (int a = 0; a < A; ++a) acc += r1[Z + a * Z + c];
+      mean[r] = acc / (float)A;
     }
-    {  // online(s')
-      const float* r = zw + N2;
-      float mean = 0.0f;
-      for (int a = 0; a < A; ++a) mean += r[Z + a * Z + c];
-      mean = mean / (float)A;
-      for (int a = 0; a < A; ++a) q_ns[a * Z + c] = r[c] + r[Z + a * Z + c] - mean;
-    }
-    {  // target(s')
-      const float* r = zw + 2 * N2;
-      float mean = 0.0f;
-      for (int a = 0; a < A; ++a) mean += r[Z + a * Z + c];
-      mean = mean / (float)A;
-      for (int a = 0; a < A; ++a) q_t[a * Z + c] = r[c] + r[Z + a * Z + c] - mean;
+    for (int a = warp; a < A; a += C51D_T / 32) {
+      float x[C51_R];
+#pragma unroll
+      for (int r = 0; r < C51_R; ++r) {
+        const int c = lane + 32 * r;
+        x[r] = (c < Z) ? r1[c] + r1[Z + a * Z + c] - mean[r] : -CUDART_INF_F;
+      }
+      const float ev = c51_expected_value<C51_R>(x, sup, Z, lane);
+      if (lane == 0) s_ev[a] = ev;
     }
   }
-  __syncwarp();
-  float g[C51_R];
-  c51_core<C51_R>(s_sc[warp], lane, i, B, A, Z, q_ns, q_t, q_s, __ldg(returns + i), __ldg(nonterminals + i), __ldg(weights + i),
-           support, vmin, vmax, delta_z, gamma_n, loss, m_out, astar_out, g);
-  float* dzi = dz + (size_t)i * N2;
+  __syncthreads();
+  if (warp == 0) {  // phase 2
+    int best = 0;
+    float best_ev = -CUDART_INF_F;
+    for (int a = 0; a < A; ++a) {
+      const float ev = s_ev[a];
+      if (ev > best_ev) {  // first maximum wins, like torch.argmax
+        best_ev = ev;
+        best = a;
+      }
+    }
+    for (int c = lane; c < Z; c += 32) {
+      {  // online(s): the taken action only
+        const float* r = zs;
+        float mean = 0.0f;
+        for (int a = 0; a < A; ++a) mean += r[Z + a * Z + c];
+        q_s[c] = r[c] + r[Z + act * Z + c] - mean / (float)A;
+      }
+      {  // target(s') at a*
+        const float* r = zs + 2 * N2;
+        float mean = 0.0f;
+        for (int a = 0; a < A; ++a) mean += r[Z + a * Z + c];
+        mean = mean / (float)A;
+        q_t[c] = r[c] + r[Z + best * Z + c] - mean;
+      }
+    }
+    __syncwarp();
+    float g[C51_R];
+    c51_core<C51_R>(s_sc, lane, i, B, A, Z, nullptr, q_t, q_s, __ldg(returns + i), __ldg(nonterminals + i), __ldg(weights + i),
+                    support, vmin, vmax, delta_z, gamma_n, loss, m_out, astar_out, g, best);
 #pragma unroll
-  for (int r = 0; r < C51_R; ++r) {
-    const int c = lane + 32 * r;
-    if (c < Z) {
-      dzi[c] = g[r];
-      for (int a = 0; a < A; ++a) dzi[Z + a * Z + c] = g[r] * ((a == act ? 1.0f : 0.0f) - inv_a);
+    for (int r = 0; r < C51_R; ++r)
+      if (lane + 32 * r < Z) s_g[lane + 32 * r] = g[r];
+  }
+  __syncthreads();
+  {  // phase 3
+    float* dzi = dz + (size_t)i * N2;
+    const float inv_a = 1.0f / (float)A;
+    for (int idx = tid; idx < N2; idx += C51D_T) {
+      if (idx < Z) {
+        dzi[idx] = s_g[idx];
+      } else {
+        const int a = (idx - Z) / Z, c = (idx - Z) - a * Z;
+        dzi[idx] = s_g[c] * ((a == act ? 1.0f : 0.0f) - inv_a);
+      }
     }
   }
 }
@@ -1560,21 +1611,20 @@ int rb_c51_dueling_loss_grad(const float* z_online, const float* z_target, int a
   const int Z = atoms, A = actions_n;
   if (B <= 0 || A <= 0 || Z <= 1) return fail(RB_ERR_INVAL, "rb_c51_dueling_loss_grad: B, actions > 0 and atoms > 1 are required");
   if (Z > RB_MAX_ATOMS) return fail(RB_ERR_RANGE, "rb_c51_dueling_loss_grad: atoms exceeds RB_MAX_ATOMS");
-  const size_t smem = (size_t)C51_WARPS * (3 * (Z + A * Z) + 2 * A * Z + Z) * sizeof(float);
+  const size_t smem = (size_t)(3 * (Z + A * Z) + 3 * Z + A) * sizeof(float);
   if (smem > 200 * 1024) return fail(RB_ERR_RANGE, "rb_c51_dueling_loss_grad: actions * atoms too large");
   int rc_s = rbi::ensure_dynamic_smem(k_c51_dueling<2>, smem, "rb_c51_dueling_loss_grad");
   if (rc_s == RB_OK) rc_s = rbi::ensure_dynamic_smem(k_c51_dueling<4>, smem, "rb_c51_dueling_loss_grad");
   if (rc_s != RB_OK) return rc_s;
-  const int ctas = (B + C51_WARPS - 1) / C51_WARPS;
   { ProfScope prof_(RB_K_C51_DUELING, (cudaStream_t)stream);
     if (Z <= 64)
-      k_c51_dueling<2><<<ctas, C51_WARPS * 32, smem, (cudaStream_t)stream>>>(z_online, z_target, actions, returns, nonterminals,
-                                                                           weights, support, vmin, vmax, delta_z, gamma_n, B, A,
-                                                                           Z, loss, dz, m_out, astar_out);
+      k_c51_dueling<2><<<B, C51D_T, smem, (cudaStream_t)stream>>>(z_online, z_target, actions, returns, nonterminals, weights,
+                                                                  support, vmin, vmax, delta_z, gamma_n, B, A, Z, loss, dz, m_out,
+                                                                  astar_out);
     else
-      k_c51_dueling<4><<<ctas, C51_WARPS * 32, smem, (cudaStream_t)stream>>>(z_online, z_target, actions, returns, nonterminals,
-                                                                           weights, support, vmin, vmax, delta_z, gamma_n, B, A,
-                                                                           Z, loss, dz, m_out, astar_out); }
+      k_c51_dueling<4><<<B, C51D_T, smem, (cudaStream_t)stream>>>(z_online, z_target, actions, returns, nonterminals, weights,
+                                                                  support, vmin, vmax, delta_z, gamma_n, B, A, Z, loss, dz, m_out,
+                                                                  astar_out); }
   return check_launch("rb_c51_dueling_loss_grad");
 }
 

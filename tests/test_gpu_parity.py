@@ -604,7 +604,7 @@ def test_fused_head_backward(arch, hidden, actions, B):
         p.grad = torch.full_like(p, 123.0)       # must be overwritten, not accumulated
     with torch.no_grad():
         z, h, p_ = net.head().forward(feats.detach())
-        dh = torch.empty(B, 2 * hidden, device=DEV)
+        dh = torch.empty(B + 32, 2 * hidden, device=DEV)   # dh [B][2H], then dhT [2H][32]
         dx = torch.empty(B, K1, device=DEV)
         net.head().backward(p_, feats.detach(), h[:B], dz, dh, dx)
     scale = lambda t: float(t.abs().max()) + 1e-12
