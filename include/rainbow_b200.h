@@ -73,7 +73,7 @@ enum {
   RB_K_TREE_UPDATE = 0, RB_K_TREE_FIND, RB_K_TREE_SAMPLE, RB_K_GATHER, RB_K_ITER_STATES, RB_K_APPEND, RB_K_C51,
   RB_K_NOISY_RESAMPLE, RB_K_NOISY_COMPOSE, RB_K_SQNORM, RB_K_CLIP_ADAM, RB_K_HEAD_FC1, RB_K_HEAD_FC2, RB_K_HEAD_LOGITS,
   RB_K_HEAD_WGRAD2, RB_K_HEAD_DH, RB_K_HEAD_BWD1, RB_K_NOISE_FACTORS, RB_K_C51_DUELING, RB_K_BIAS_GRAD, RB_K_Q_VALUES,
-  RB_K_HEAD_REDUCE1, RB_KERNEL_COUNT
+  RB_K_HEAD_REDUCE1, RB_K_CONV_WGRAD, RB_KERNEL_COUNT
 };
 
 int rb_abi_version(void);
@@ -246,6 +246,15 @@ int rb_q_values(const float* z, int M, int actions, int atoms, const float* supp
 /* Bias gradient of a conv layer (the sum over batch and pixels torch computes in convolution_backward):
  * out[c] = sum_{b,p} grad_out[b][c][p], grad_out float32[B][C][HW] contiguous. */
 int rb_bias_grad(const float* grad_out, int B, int C, int HW, float* out, rb_stream_t stream);
+
+/* Weight gradient of a conv layer whose data gradient is not needed (the network's first layer; the weight half of
+ * torch's convolution_backward there): out[oc][ic][ky][kx] = sum_{b,y,x} grad_out[b][oc][y][x] * input[b][ic][y*stride+ky][x*stride+kx]
+ * for a square K x K kernel without padding (K in {3, 4, 5, 8}; IC * K * ceil(OC/4) <= 256).  grad_out float32
+ * [B][OC][OH][OW], input float32 [B][IC][IH][IW] (OH = (IH-K)/stride + 1), out float32 [OC][IC][K][K] (overwritten),
+ * partials: scratch of rb_conv_wgrad_scratch_elems(...) floats.  Two launches, fixed summation order (deterministic). */
+int rb_conv_wgrad_scratch_elems(int B, int IC, int IH, int OC, int K, int stride);
+int rb_conv_wgrad(const float* grad_out, const float* input, int B, int IC, int IH, int IW, int OC, int K, int stride,
+                  float* partials, float* out, rb_stream_t stream);
 
 /* rb_c51_loss_grad fed by the fused heads: z_online has 2B rows (s then s'), z_target B rows (s');
  * returns loss[B] and dz[B][atoms*(1+actions)] = d mean(w*loss) / d (z_value | z_advantage) of the online(s) rows

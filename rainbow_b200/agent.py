@@ -172,6 +172,7 @@ class Agent:
             self.online_net.load_state_dict(state_dict)
             print("Loading pretrained model: " + model_path)
         self.online_net.train()
+        self.online_net.lazy_noise = True   # reset_noise() is launched at its first use / on a side branch of the update
 
         self.target_net = DQN(args, self.action_space).to(device=self.device)
         self.sync = GradSync()  # no-op unless torch.distributed is initialised with world_size > 1
@@ -192,11 +193,11 @@ class Agent:
 
         self.use_cuda_graph = bool(getattr(args, "cuda_graph", True))
         self.use_fused_head = bool(getattr(args, "fused_head", True))
+        self.batch_online_convs = bool(getattr(args, "batch_online_convs", True))
         self._step_gate = None
         self._streams = None
-        self._graph = None
+        self._graphs = {}         # online-noise-pending flag -> (captured update graph, its sample workspace, its loss tensor)
         self._graph_key = None    # (weakref to the memory the graph was captured for, batch size)
-        self._ws = None
         self._learn_calls = 0
         self._rejected_seen = 0
         self._q_graphs = {}       # training-mode flag -> captured one-state act / evaluate_q graph
@@ -233,6 +234,7 @@ class Agent:
         (action int64[1], value float32[1]) after ONE device-to-host copy and one event wait -- the per-env-step cost of
         main.py:139,153 / test.py:26 instead of ~40 eager launches and a blocking .item()."""
         on = self.online_net
+        on.flush_noise()            # a deferred reset_noise() must not be captured into (and redrawn by) the act graph
         key = bool(on.training)
         g = self._q_graphs.get(key)
         if g is None:
@@ -311,6 +313,17 @@ class Agent:
         on = self.online_net
         return self.use_fused_head and B <= 32 and on.training and on.fused_ok(2 * B) and self.target_net.fused_ok(B)
 
+    @staticmethod
+    def _adjacent(states, next_states):
+        """The [2B, ...] tensor whose halves are `states` and `next_states`, if they are laid out that way."""
+        if (states.is_contiguous() and next_states.is_contiguous() and states.shape == next_states.shape and
+                next_states.data_ptr() == states.data_ptr() + states.numel() * states.element_size() and
+                states._base is not None and states._base is next_states._base):
+            base = states._base
+            if base.data_ptr() == states.data_ptr() and base.numel() == 2 * states.numel():
+                return base.view((2 * states.shape[0],) + tuple(states.shape[1:]))
+        return None
+
     def _side_streams(self):
         if self._streams is None:
             self._streams = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
@@ -329,6 +342,13 @@ class Agent:
         s_ns, s_tg = self._side_streams()
         fork = torch.cuda.Event()
         fork.record(main)
+        noise_done = None
+        if on._noise_pending:   # the online net's deferred reset_noise(): beside the sampling / conv work, not in front of it
+            with torch.cuda.stream(s_ns):
+                s_ns.wait_event(fork)
+                on.flush_noise()
+                noise_done = torch.cuda.Event()
+                noise_done.record(s_ns)
         with torch.cuda.stream(s_tg), torch.no_grad():
             s_tg.wait_event(fork)
             if target_noise is None:
@@ -339,24 +359,41 @@ class Agent:
             z_t, _, _ = tg.head().forward(x_t)
             done_tg = torch.cuda.Event()
             done_tg.record(s_tg)
-        with torch.cuda.stream(s_ns), torch.no_grad():
-            s_ns.wait_event(fork)
-            x_ns = on.features_nograd(next_states)
-            done_ns = torch.cuda.Event()
-            done_ns.record(s_ns)
         manual = on.manual_conv_ok(states)
-        if manual:
+        # [s; s'] in ONE conv pass when the sampler laid both state blocks out back to back (ReplayMemory's workspaces do):
+        # the online net's weights stream once, and two concurrent conv chains (online, target) share the SMs instead of three
+        both = self._adjacent(states, next_states) if (manual and self.batch_online_convs) else None
+        if both is not None:
             with torch.no_grad():
-                acts = on.conv_forward_saving(states)  # library kernels, backward scheduled by hand below
-            x_s = acts[-1].view(B, -1)
+                acts2 = on.conv_forward_saving(both)
+                acts = [a[:B] for a in acts2]              # the s half (batch-major: contiguous slices) feeds the backward
+                x_both = acts2[-1].view(2 * B, -1)
+                x_s, xs_d = x_both[:B], x_both[:B]
+                if noise_done is not None:
+                    main.wait_event(noise_done)
+                z_on, h_on, p_on = on.head().forward(x_both)              # rows [0,B) = s, [B,2B) = s'
+                main.wait_event(done_tg)
         else:
-            x_s = on.features(states)                  # autograd graph: convs only
+            with torch.cuda.stream(s_ns), torch.no_grad():
+                s_ns.wait_event(fork)
+                x_ns = on.features_nograd(next_states)
+                done_ns = torch.cuda.Event()
+                done_ns.record(s_ns)
+            if manual:
+                with torch.no_grad():
+                    acts = on.conv_forward_saving(states)  # library kernels, backward scheduled by hand below
+                x_s = acts[-1].view(B, -1)
+            else:
+                x_s = on.features(states)                  # autograd graph: convs only
+            with torch.no_grad():
+                xs_d = x_s.detach()
+                main.wait_event(done_ns)
+                if noise_done is not None:
+                    main.wait_event(noise_done)
+                x_ns.record_stream(main)
+                z_on, h_on, p_on = on.head().forward(xs_d, x_ns)              # rows [0,B) = s, [B,2B) = s'
+                main.wait_event(done_tg)
         with torch.no_grad():
-            xs_d = x_s.detach()
-            main.wait_event(done_ns)
-            x_ns.record_stream(main)
-            z_on, h_on, p_on = on.head().forward(xs_d, x_ns)              # rows [0,B) = s, [B,2B) = s'
-            main.wait_event(done_tg)
             loss, dz = c51_dueling_loss_grad(z_on, z_t, self.action_space, self.atoms, actions, returns, nonterminals, weights,
                                              self.support, self.Vmin, self.Vmax, self.delta_z, self.discount ** self.n)
             wb_done = None
@@ -464,7 +501,12 @@ class Agent:
             batch = mem.sample_into(ws)
             loss = self._update_from_batch(batch, after_loss=lambda l: mem.update_priorities(batch[0], l, gate=ws.status),
                                            gate=ws.status)
-        self._graph, self._ws, self.last_loss = graph, ws, loss
+        return graph, ws, loss
+
+    @property
+    def _graph(self):
+        """Any captured update graph (None before the first capture)."""
+        return next(iter(self._graphs.values()))[0] if self._graphs else None
 
     GRAPH_WARMUP = 2  # eager updates before capture (cuDNN/cuBLAS plan selection, autograd buffers)
 
@@ -478,10 +520,10 @@ class Agent:
         # weak reference: the agent must not keep a dropped 7 GB replay alive; a dead or different referent, or another
         # batch size, invalidates the captured graph (a recycled id() can never alias a dead memory's graph)
         if graphable and (self._graph_key is None or self._graph_key[0]() is not mem or self._graph_key[1] != self.batch_size):
-            self._graph, self._ws, self._graph_key, self._warm = None, None, (weakref.ref(mem), self.batch_size), 0
+            self._graphs, self._graph_key, self._warm = {}, (weakref.ref(mem), self.batch_size), 0
         if not graphable:
             self.last_loss = self._learn_eager(mem)
-        elif self._graph is None and self._warm < self.GRAPH_WARMUP:
+        elif not self._graphs and self._warm < self.GRAPH_WARMUP:
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
@@ -489,11 +531,18 @@ class Agent:
             torch.cuda.current_stream(self.device).wait_stream(side)
             self._warm += 1
         else:
-            if self._graph is None:
-                self._capture(mem)
+            # two variants of the graph: with the online net's deferred reset_noise() as a side branch (the usual
+            # `reset_noise(); learn()` pair) and without it (an act() in between has already launched the draw)
+            pending = bool(self.online_net._noise_pending)
+            if pending not in self._graphs:
+                self._graphs[pending] = self._capture(mem)
+            graph, ws, loss = self._graphs[pending]
             mem.flush_appends()   # no-op unless the memory defers its appends
             mem.push_beta()
-            self._graph.replay()
+            graph.replay()
+            self.online_net._noise_pending = False
+            self.online_net._eps_stale = self.online_net._eps_stale or pending
+            self.last_loss, mem._last = loss, ws
         self._learn_calls += 1
         if self._learn_calls % 4096 == 0 and isinstance(mem, ReplayMemory):
             # diagnostics only (the device already skipped such updates): how many batches stayed invalid after

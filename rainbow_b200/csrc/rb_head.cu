@@ -843,6 +843,98 @@ k_bias_grad(const float* __restrict__ g, int B, int C, int HW, float* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight gradient of the FIRST conv layer (no data gradient follows it, so in the hand-scheduled backward this is the one
+// library launch left alone on the critical path: cuDNN's wgrad_alg0_engine takes 31 us for 105 MFLOP at batch 32):
+//   dW[oc][ic][ky][kx] = sum_{b,y,x} g[b][oc][y][x] * in[b][ic][y*S + ky][x*S + kx]            (fp32 FMA, fixed order)
+// grid = (bands of output rows, B): a CTA stages its slab of the input (the rows its band touches, all channels) and of g
+// in shared memory with every load in flight at once, thread (oc group, kernel row (ic, ky)) accumulates a 4 x KW register
+// tile over the band's positions, and the per-CTA partial tiles are summed in CTA order by k_conv_wgrad_reduce
+// (deterministic; the partials stay in L2).
+// ------------------------------------------------------------------------------------------------
+constexpr int CW_OCT = 4;   // output channels per thread
+
+template <int KW>
+__global__ void __launch_bounds__(256)
+k_conv_wgrad_first(const float* __restrict__ g, const float* __restrict__ in, int IC, int IH, int IW, int OC, int OH, int OW,
+                   int S, int RB, float* __restrict__ part) {
+  extern __shared__ __align__(16) float cw_smem[];
+  const int band = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
+  const int y0 = band * RB, rows = min(RB, OH - y0);          // output rows [y0, y0 + rows)
+  const int in_rows = (RB - 1) * S + KW;                       // input rows a full band touches (square kernel)
+  const int xs_ld = in_rows * IW;                              // floats per channel slab
+  float* xs = cw_smem;                                         // [IC][in_rows][IW]
+  float* gs = cw_smem + (size_t)IC * xs_ld;                    // [OC][RB * OW]
+  const int have_rows = min(in_rows, IH - y0 * S);
+  for (int ic = 0; ic < IC; ++ic) {                            // contiguous in global memory per channel
+    const float* src = in + ((size_t)(b * IC + ic) * IH + (size_t)y0 * S) * IW;
+    for (int i = tid; i < have_rows * IW; i += nthr) xs[ic * xs_ld + i] = __ldg(src + i);
+  }
+  for (int oc = 0; oc < OC; ++oc) {
+    const float* src = g + ((size_t)(b * OC + oc) * OH + y0) * OW;
+    for (int i = tid; i < rows * OW; i += nthr) gs[oc * (RB * OW) + i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const bool vec = (S % 4 == 0) && (IW % 4 == 0);
+  const int krows = IC * KW;                                    // kernel rows (ic, ky)
+  const int kr = tid % krows, og = tid / krows;                 // this thread: kernel row kr, channels og*4 .. og*4+3
+  const int ic = kr / KW, ky = kr % KW;
+  float acc[CW_OCT][KW];
+#pragma unroll
+  for (int i = 0; i < CW_OCT; ++i)
+#pragma unroll
+    for (int j = 0; j < KW; ++j) acc[i][j] = 0.0f;
+  if (og * CW_OCT < OC) {
+    for (int yy = 0; yy < rows; ++yy) {
+      const float* xrow = xs + ic * xs_ld + (yy * S + ky) * IW;
+      const float* grow = gs + (og * CW_OCT) * (RB * OW) + yy * OW;
+      for (int xx = 0; xx < OW; ++xx) {
+        float xv[KW], gv[CW_OCT];
+        if ((KW % 4 == 0) && vec) {   // 16-byte aligned kernel rows (stride and row pitch multiples of 4 floats)
+#pragma unroll
+          for (int j = 0; j < KW; j += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(xrow + xx * S + j);
+            xv[j] = v.x; xv[j + 1] = v.y; xv[j + 2] = v.z; xv[j + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < KW; ++j) xv[j] = xrow[xx * S + j];
+        }
+#pragma unroll
+        for (int i = 0; i < CW_OCT; ++i) gv[i] = grow[i * (RB * OW) + xx];
+#pragma unroll
+        for (int i = 0; i < CW_OCT; ++i)
+#pragma unroll
+          for (int j = 0; j < KW; ++j) acc[i][j] = fmaf(gv[i], xv[j], acc[i][j]);
+      }
+    }
+    float* dst = part + (size_t)(b * gridDim.x + band) * ((size_t)OC * IC * KW * KW);
+#pragma unroll
+    for (int i = 0; i < CW_OCT; ++i) {
+      const int oc = og * CW_OCT + i;
+      if (oc < OC) {
+#pragma unroll
+        for (int j = 0; j < KW; ++j) dst[((size_t)(oc * IC + ic) * KW + ky) * KW + j] = acc[i][j];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_conv_wgrad_reduce(const float* __restrict__ part, int n_part, int n, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float acc = 0.0f;
+  for (int p0 = 0; p0 < n_part; p0 += 16) {       // sixteen loads in flight, summed in CTA order
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = (p0 + u < n_part) ? __ldcg(part + (size_t)(p0 + u) * n + j) : 0.0f;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) acc += v[u];
+  }
+  out[j] = acc;
+}
+
 int head_check(const rb_head_params* p, const char* who) {
   if (!p) return rbi::fail(RB_ERR_INVAL, who);
   for (int s = 0; s < 2; ++s)
@@ -1022,6 +1114,42 @@ int rb_bias_grad(const float* grad_out, int B, int C, int HW, float* out, rb_str
     k_bias_grad<<<C, 256, 0, (cudaStream_t)stream>>>(grad_out, B, C, HW, out);
   }
   return rbi::check_launch("rb_bias_grad");
+}
+
+static int conv_wgrad_band_rows(int OH) { return OH >= 16 ? (OH + 3) / 4 : OH; }   // 4 bands of output rows per sample
+
+int rb_conv_wgrad_scratch_elems(int B, int IC, int IH, int OC, int K, int stride) {
+  if (B <= 0 || IC <= 0 || OC <= 0 || K <= 0 || stride <= 0 || IH < K) return 0;
+  const int OH = (IH - K) / stride + 1, RB = conv_wgrad_band_rows(OH), bands = (OH + RB - 1) / RB;
+  return B * bands * OC * IC * K * K;
+}
+
+int rb_conv_wgrad(const float* grad_out, const float* input, int B, int IC, int IH, int IW, int OC, int K, int stride,
+                  float* partials, float* out, rb_stream_t stream) {
+  if (!grad_out || !input || !partials || !out) return rbi::fail(RB_ERR_INVAL, "rb_conv_wgrad: null pointer");
+  if (B <= 0 || IC <= 0 || OC <= 0 || stride <= 0 || IH < K || IW < K) return rbi::fail(RB_ERR_INVAL, "rb_conv_wgrad: bad shape");
+  if (K != 8 && K != 5 && K != 4 && K != 3) return rbi::fail(RB_ERR_RANGE, "rb_conv_wgrad: kernel sizes 3, 4, 5 and 8 are instantiated");
+  const int OH = (IH - K) / stride + 1, OW = (IW - K) / stride + 1;
+  const int RB = conv_wgrad_band_rows(OH), bands = (OH + RB - 1) / RB;
+  const int threads = IC * K * ((OC + CW_OCT - 1) / CW_OCT);
+  if (threads > 256 || B > 65535) return rbi::fail(RB_ERR_RANGE, "rb_conv_wgrad: IC * K * ceil(OC / 4) must not exceed 256 threads");
+  const size_t smem = ((size_t)IC * ((RB - 1) * stride + K) * IW + (size_t)OC * RB * OW) * sizeof(float);
+  if (smem > 200 * 1024) return rbi::fail(RB_ERR_RANGE, "rb_conv_wgrad: slab does not fit in shared memory");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(bands, B);
+  int rc = RB_OK;
+  {
+    rbi::ProfScope prof_(RB_K_CONV_WGRAD, st);
+#define RB_CW_LAUNCH(KW_)                                                                                              \
+  rc = rbi::ensure_dynamic_smem(k_conv_wgrad_first<KW_>, smem, "rb_conv_wgrad");                                       \
+  if (rc == RB_OK) k_conv_wgrad_first<KW_><<<grid, threads, smem, st>>>(grad_out, input, IC, IH, IW, OC, OH, OW, stride, RB, partials);
+    if (K == 8) { RB_CW_LAUNCH(8) } else if (K == 5) { RB_CW_LAUNCH(5) } else if (K == 4) { RB_CW_LAUNCH(4) } else { RB_CW_LAUNCH(3) }
+#undef RB_CW_LAUNCH
+    if (rc != RB_OK) return rc;
+    const int n = OC * IC * K * K;
+    k_conv_wgrad_reduce<<<(n + 255) / 256, 256, 0, st>>>(partials, B * bands, n, out);
+  }
+  return rbi::check_launch("rb_conv_wgrad");
 }
 
 int rb_noise_factors(float* f_in, int n_in, float* f_out, int n_out, const float* x_in, const float* x_out, uint64_t seed,

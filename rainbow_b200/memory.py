@@ -202,8 +202,9 @@ class _SampleWorkspace:
         self.data_idx = torch.empty(B, dtype=i64, device=device)
         self.tree_idx = torch.empty(B, dtype=i64, device=device)
         self.weights = torch.empty(B, dtype=f32, device=device)
-        self.states = torch.empty((B, history, 84, 84), dtype=f32, device=device)
-        self.next_states = torch.empty((B, history, 84, 84), dtype=f32, device=device)
+        # one allocation, s rows then s' rows: the learner can push [s; s'] through the online conv body in a single pass
+        self.both_states = torch.empty((2 * B, history, 84, 84), dtype=f32, device=device)
+        self.states, self.next_states = self.both_states[:B], self.both_states[B:]
         self.actions = torch.empty(B, dtype=i64, device=device)
         self.returns = torch.empty(B, dtype=f32, device=device)
         self.nonterminals = torch.empty((B, 1), dtype=f32, device=device)

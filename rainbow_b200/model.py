@@ -203,9 +203,15 @@ class DQN(nn.Module):
         self.register_buffer("_f_in", torch.cat([m._f_in for m in layers]), persistent=False)
         self.register_buffer("_f_out", torch.cat([m._f_out for m in layers]), persistent=False)
         self._noise_queue = []   # parity facility: injected raw normals consumed by the next reset_noise() calls
+        # lazy_noise (set by the learner for its online net): an argument-less reset_noise() only marks the draw as pending;
+        # it is launched by flush_noise() right before its first use (act / evaluate / state_dict), or by the learner on a
+        # side branch of the update instead of serially in front of it.  Same draws, same order, nothing skipped.
+        self.lazy_noise = False
+        self._noise_pending = False
         self._eps_stale = False  # weight_epsilon / bias_epsilon buffers currently equal the outer product of the factors
         self._head = None
         self.use_fused_head = True
+        self.use_own_wgrad = True     # first conv layer's weight gradient through rb_conv_wgrad (else cuDNN)
 
     # ---- noise ---------------------------------------------------------------------------------------
     def noisy_layers(self):
@@ -213,6 +219,7 @@ class DQN(nn.Module):
         return [m for name, m in self.named_children() if "fc" in name]
 
     def noise_factors(self):
+        self.flush_noise()
         out, oi, oo = {}, 0, 0
         for name, m in self.named_children():
             if "fc" in name:
@@ -227,10 +234,24 @@ class DQN(nn.Module):
             raise _lib.RainbowB200Error("DQN.reset_noise needs the network on a CUDA device (no CPU fallback)")
         if x_in is None and self._noise_queue:
             x_in, x_out = self._noise_queue.pop(0)
+        if x_in is None and self.lazy_noise and not torch.cuda.is_current_stream_capturing():
+            self._noise_pending = True
+            return
+        self._noise_pending = False
         _lib.check(_lib.load().rb_noise_factors(_lib.ptr(self._f_in), self._f_in.numel(), _lib.ptr(self._f_out),
                                                 self._f_out.numel(), _lib.ptr(x_in), _lib.ptr(x_out), self.noise_seed,
                                                 _lib.ptr(self._noise_counter), _lib.stream()))
         self._eps_stale = True
+
+    def flush_noise(self):
+        """Launch a reset_noise() that was deferred (lazy_noise)."""
+        if self._noise_pending:
+            self._noise_pending = False
+            lazy, self.lazy_noise = self.lazy_noise, False
+            try:
+                self.reset_noise()
+            finally:
+                self.lazy_noise = lazy
 
     def queue_noise(self, x_in, x_out):
         """Parity testing: the next argument-less reset_noise() uses these raw standard normals (device float32, all
@@ -240,6 +261,7 @@ class DQN(nn.Module):
 
     def materialise_noise(self):
         """Bring weight_epsilon / bias_epsilon (model.py:39-40) up to date with the factor vectors."""
+        self.flush_noise()
         if self._eps_stale:
             w, b, fin, fout, n = _layer_arrays(self.noisy_layers())
             _lib.check(_lib.load().rb_noisy_outer(w, b, fin, fout, n, _lib.ptr(self._f_in), _lib.ptr(self._f_out),
@@ -261,12 +283,15 @@ class DQN(nn.Module):
         self._eps_stale = False
 
     def state_dict(self, *args, **kwargs):
+        if self._f_in.is_cuda:
+            self.flush_noise()
         if self._eps_stale and self._f_in.is_cuda:
             self.materialise_noise()
         return super().state_dict(*args, **kwargs)
 
     def load_state_dict(self, state_dict, *args, **kwargs):
         out = super().load_state_dict(state_dict, *args, **kwargs)
+        self._noise_pending = False          # the loaded epsilon buffers supersede a deferred draw
         self._factors_from_buffers()
         return out
 
@@ -297,6 +322,21 @@ class DQN(nn.Module):
             acts.append(torch.cudnn_convolution_relu(acts[-1], m.weight, m.bias, m.stride, m.padding, m.dilation, m.groups))
         return acts
 
+    def _own_wgrad_ok(self, m, a_in):
+        k, s = m.kernel_size, m.stride
+        return (self.use_own_wgrad and k[0] == k[1] and s[0] == s[1] and k[0] in (3, 4, 5, 8) and tuple(m.padding) == (0, 0) and
+                tuple(m.dilation) == (1, 1) and m.groups == 1 and a_in.is_contiguous() and m.weight.grad.is_contiguous() and
+                m.in_channels * k[0] * ((m.out_channels + 3) // 4) <= 256 and
+                _lib.load().rb_conv_wgrad_scratch_elems(a_in.shape[0], m.in_channels, a_in.shape[2], m.out_channels, k[0], s[0]) > 0)
+
+    def _wgrad_scratch(self, m, a_in):
+        n = _lib.load().rb_conv_wgrad_scratch_elems(a_in.shape[0], m.in_channels, a_in.shape[2], m.out_channels, m.kernel_size[0], m.stride[0])
+        buf = getattr(self, "_wgrad_buf", None)
+        if buf is None or buf.numel() < n or buf.device != a_in.device:
+            buf = torch.empty(n, dtype=torch.float32, device=a_in.device)
+            self._wgrad_buf = buf
+        return buf
+
     def conv_backward_into_grads(self, acts, g_last, side_stream):
         """Backward of the conv body given g_last = d loss / d (pre-activation of the last conv layer).
         The data-gradient chain (dgrad -> ReLU mask -> dgrad ...) runs on the current stream; the weight and bias
@@ -313,11 +353,19 @@ class DQN(nn.Module):
             with torch.cuda.stream(side_stream):
                 side_stream.wait_event(ready)
                 g.record_stream(side_stream)
-                _, gw, _ = torch.ops.aten.convolution_backward(g, a_in, m.weight, None, m.stride, m.padding, m.dilation, False,
-                                                               [0, 0], m.groups, [False, True, False])
-                m.weight.grad.copy_(gw)
+                # bias first (it only needs g), then the weight gradient
                 _lib.check(lib.rb_bias_grad(_lib.ptr(g), g.shape[0], g.shape[1], g.shape[2] * g.shape[3],
                                             _lib.ptr(m.bias.grad), side_stream.cuda_stream))
+                if li == 0 and self._own_wgrad_ok(m, a_in):
+                    # first layer: no data gradient follows, so this launch sits alone on the critical path -> own kernel
+                    # (csrc/rb_head.cu k_conv_wgrad_first: 9 us instead of cuDNN's 31 us at batch 32)
+                    _lib.check(lib.rb_conv_wgrad(_lib.ptr(g), _lib.ptr(a_in), a_in.shape[0], a_in.shape[1], a_in.shape[2], a_in.shape[3],
+                                                 m.out_channels, m.kernel_size[0], m.stride[0], _lib.ptr(self._wgrad_scratch(m, a_in)),
+                                                 _lib.ptr(m.weight.grad), side_stream.cuda_stream))
+                else:
+                    _, gw, _ = torch.ops.aten.convolution_backward(g, a_in, m.weight, None, m.stride, m.padding, m.dilation, False,
+                                                                   [0, 0], m.groups, [False, True, False])
+                    m.weight.grad.copy_(gw)
             if li > 0:
                 gin, _, _ = torch.ops.aten.convolution_backward(g, a_in, m.weight, None, m.stride, m.padding, m.dilation, False,
                                                                 [0, 0], m.groups, [True, False, False])
