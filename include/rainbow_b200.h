@@ -251,10 +251,11 @@ int rb_bias_grad(const float* grad_out, int B, int C, int HW, float* out, rb_str
  * torch's convolution_backward there): out[oc][ic][ky][kx] = sum_{b,y,x} grad_out[b][oc][y][x] * input[b][ic][y*stride+ky][x*stride+kx]
  * for a square K x K kernel without padding (K in {3, 4, 5, 8}; IC * K * ceil(OC/4) <= 256).  grad_out float32
  * [B][OC][OH][OW], input float32 [B][IC][IH][IW] (OH = (IH-K)/stride + 1), out float32 [OC][IC][K][K] (overwritten),
+ * bias_out (optional, may be NULL) float32 [OC] = sum_{b,y,x} grad_out (the layer's bias gradient, from the same pass),
  * partials: scratch of rb_conv_wgrad_scratch_elems(...) floats.  Two launches, fixed summation order (deterministic). */
 int rb_conv_wgrad_scratch_elems(int B, int IC, int IH, int OC, int K, int stride);
 int rb_conv_wgrad(const float* grad_out, const float* input, int B, int IC, int IH, int IW, int OC, int K, int stride,
-                  float* partials, float* out, rb_stream_t stream);
+                  float* partials, float* out, float* bias_out, rb_stream_t stream);
 
 /* rb_c51_loss_grad fed by the fused heads: z_online has 2B rows (s then s'), z_target B rows (s');
  * returns loss[B] and dz[B][atoms*(1+actions)] = d mean(w*loss) / d (z_value | z_advantage) of the online(s) rows

@@ -866,15 +866,32 @@ k_conv_wgrad_first(const float* __restrict__ g, const float* __restrict__ in, in
   float* xs = cw_smem;                                         // [IC][in_rows][IW]
   float* gs = cw_smem + (size_t)IC * xs_ld;                    // [OC][RB * OW]
   const int have_rows = min(in_rows, IH - y0 * S);
-  for (int ic = 0; ic < IC; ++ic) {                            // contiguous in global memory per channel
-    const float* src = in + ((size_t)(b * IC + ic) * IH + (size_t)y0 * S) * IW;
-    for (int i = tid; i < have_rows * IW; i += nthr) xs[ic * xs_ld + i] = __ldg(src + i);
-  }
-  for (int oc = 0; oc < OC; ++oc) {
-    const float* src = g + ((size_t)(b * OC + oc) * OH + y0) * OW;
-    for (int i = tid; i < rows * OW; i += nthr) gs[oc * (RB * OW) + i] = __ldg(src + i);
+  const int n_w = OC * IC * KW * KW;
+  // both slabs are contiguous per channel in global memory; cp.async keeps every 16-byte chunk in flight at once
+  const bool al = (IW % 4 == 0) && (OW % 4 == 0) && ((((uintptr_t)g | (uintptr_t)in) & 15) == 0);
+  if (al) {
+    const int xc = have_rows * IW / 4, gc = rows * OW / 4;
+    for (int i = tid; i < IC * xc; i += nthr) {
+      const int ic = i / xc, c = i - ic * xc;
+      cp_async16(xs + ic * xs_ld + 4 * c, in + ((size_t)(b * IC + ic) * IH + (size_t)y0 * S) * IW + 4 * c);
+    }
+    for (int i = tid; i < OC * gc; i += nthr) {
+      const int oc = i / gc, c = i - oc * gc;
+      cp_async16(gs + oc * (RB * OW) + 4 * c, g + ((size_t)(b * OC + oc) * OH + y0) * OW + 4 * c);
+    }
+    cp_async_wait_all();
+  } else {
+    for (int ic = 0; ic < IC; ++ic) {
+      const float* src = in + ((size_t)(b * IC + ic) * IH + (size_t)y0 * S) * IW;
+      for (int i = tid; i < have_rows * IW; i += nthr) xs[ic * xs_ld + i] = __ldg(src + i);
+    }
+    for (int oc = 0; oc < OC; ++oc) {
+      const float* src = g + ((size_t)(b * OC + oc) * OH + y0) * OW;
+      for (int i = tid; i < rows * OW; i += nthr) gs[oc * (RB * OW) + i] = __ldg(src + i);
+    }
   }
   __syncthreads();
+  float* dst = part + (size_t)(b * gridDim.x + band) * (size_t)(n_w + OC);
   const bool vec = (S % 4 == 0) && (IW % 4 == 0);
   const int krows = IC * KW;                                    // kernel rows (ic, ky)
   const int kr = tid % krows, og = tid / krows;                 // this thread: kernel row kr, channels og*4 .. og*4+3
@@ -908,7 +925,6 @@ k_conv_wgrad_first(const float* __restrict__ g, const float* __restrict__ in, in
           for (int j = 0; j < KW; ++j) acc[i][j] = fmaf(gv[i], xv[j], acc[i][j]);
       }
     }
-    float* dst = part + (size_t)(b * gridDim.x + band) * ((size_t)OC * IC * KW * KW);
 #pragma unroll
     for (int i = 0; i < CW_OCT; ++i) {
       const int oc = og * CW_OCT + i;
@@ -918,21 +934,41 @@ k_conv_wgrad_first(const float* __restrict__ g, const float* __restrict__ in, in
       }
     }
   }
+  // bias gradient partial of this slab (sum of g over the band's positions), appended to the partial row
+  for (int oc = tid; oc < OC; oc += nthr) {
+    float bsum = 0.0f;
+    for (int i = 0; i < rows * OW; ++i) bsum += gs[oc * (RB * OW) + i];
+    dst[n_w + oc] = bsum;
+  }
 }
 
-__global__ void __launch_bounds__(256)
-k_conv_wgrad_reduce(const float* __restrict__ part, int n_part, int n, float* __restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+// out[j] = sum over the n_part per-CTA partials, in CTA order (quarters of the partials summed side by side, then combined
+// in quarter order: deterministic).  64 outputs per CTA, every load of a thread in flight at once.
+constexpr int CWR_J = 64;
+
+__global__ void __launch_bounds__(4 * CWR_J)
+k_conv_wgrad_reduce(const float* __restrict__ part, int n_part, int n_w, int n_b, float* __restrict__ out_w,
+                    float* __restrict__ out_b) {
+  __shared__ float s_q[4][CWR_J];
+  const int jl = threadIdx.x % CWR_J, q = threadIdx.x / CWR_J, j = blockIdx.x * CWR_J + jl, n = n_w + n_b;
+  const int per = (n_part + 3) / 4, p_lo = q * per, p_hi = min(n_part, p_lo + per);
   float acc = 0.0f;
-  for (int p0 = 0; p0 < n_part; p0 += 16) {       // sixteen loads in flight, summed in CTA order
-    float v[16];
+  if (j < n) {
+    for (int p0 = p_lo; p0 < p_hi; p0 += 32) {
+      float v[32];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = (p0 + u < n_part) ? __ldcg(part + (size_t)(p0 + u) * n + j) : 0.0f;
+      for (int u = 0; u < 32; ++u) v[u] = (p0 + u < p_hi) ? __ldcg(part + (size_t)(p0 + u) * n + j) : 0.0f;
 #pragma unroll
-    for (int u = 0; u < 16; ++u) acc += v[u];
+      for (int u = 0; u < 32; ++u) acc += v[u];
+    }
   }
-  out[j] = acc;
+  s_q[q][jl] = acc;
+  __syncthreads();
+  if (q == 0 && j < n) {
+    const float t = ((s_q[0][jl] + s_q[1][jl]) + s_q[2][jl]) + s_q[3][jl];
+    if (j < n_w) out_w[j] = t;
+    else if (out_b) out_b[j - n_w] = t;
+  }
 }
 
 int head_check(const rb_head_params* p, const char* who) {
@@ -1121,11 +1157,11 @@ static int conv_wgrad_band_rows(int OH) { return OH >= 16 ? (OH + 3) / 4 : OH; }
 int rb_conv_wgrad_scratch_elems(int B, int IC, int IH, int OC, int K, int stride) {
   if (B <= 0 || IC <= 0 || OC <= 0 || K <= 0 || stride <= 0 || IH < K) return 0;
   const int OH = (IH - K) / stride + 1, RB = conv_wgrad_band_rows(OH), bands = (OH + RB - 1) / RB;
-  return B * bands * OC * IC * K * K;
+  return B * bands * (OC * IC * K * K + OC);
 }
 
 int rb_conv_wgrad(const float* grad_out, const float* input, int B, int IC, int IH, int IW, int OC, int K, int stride,
-                  float* partials, float* out, rb_stream_t stream) {
+                  float* partials, float* out, float* bias_out, rb_stream_t stream) {
   if (!grad_out || !input || !partials || !out) return rbi::fail(RB_ERR_INVAL, "rb_conv_wgrad: null pointer");
   if (B <= 0 || IC <= 0 || OC <= 0 || stride <= 0 || IH < K || IW < K) return rbi::fail(RB_ERR_INVAL, "rb_conv_wgrad: bad shape");
   if (K != 8 && K != 5 && K != 4 && K != 3) return rbi::fail(RB_ERR_RANGE, "rb_conv_wgrad: kernel sizes 3, 4, 5 and 8 are instantiated");
@@ -1146,8 +1182,8 @@ int rb_conv_wgrad(const float* grad_out, const float* input, int B, int IC, int 
     if (K == 8) { RB_CW_LAUNCH(8) } else if (K == 5) { RB_CW_LAUNCH(5) } else if (K == 4) { RB_CW_LAUNCH(4) } else { RB_CW_LAUNCH(3) }
 #undef RB_CW_LAUNCH
     if (rc != RB_OK) return rc;
-    const int n = OC * IC * K * K;
-    k_conv_wgrad_reduce<<<(n + 255) / 256, 256, 0, st>>>(partials, B * bands, n, out);
+    const int n_w = OC * IC * K * K;
+    k_conv_wgrad_reduce<<<(n_w + OC + CWR_J - 1) / CWR_J, 4 * CWR_J, 0, st>>>(partials, B * bands, n_w, OC, out, bias_out);
   }
   return rbi::check_launch("rb_conv_wgrad");
 }

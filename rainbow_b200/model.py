@@ -353,16 +353,15 @@ class DQN(nn.Module):
             with torch.cuda.stream(side_stream):
                 side_stream.wait_event(ready)
                 g.record_stream(side_stream)
-                # bias first (it only needs g), then the weight gradient
-                _lib.check(lib.rb_bias_grad(_lib.ptr(g), g.shape[0], g.shape[1], g.shape[2] * g.shape[3],
-                                            _lib.ptr(m.bias.grad), side_stream.cuda_stream))
                 if li == 0 and self._own_wgrad_ok(m, a_in):
                     # first layer: no data gradient follows, so this launch sits alone on the critical path -> own kernel
-                    # (csrc/rb_head.cu k_conv_wgrad_first: 9 us instead of cuDNN's 31 us at batch 32)
+                    # (csrc/rb_head.cu k_conv_wgrad_first; weight AND bias gradient from one pass over g)
                     _lib.check(lib.rb_conv_wgrad(_lib.ptr(g), _lib.ptr(a_in), a_in.shape[0], a_in.shape[1], a_in.shape[2], a_in.shape[3],
                                                  m.out_channels, m.kernel_size[0], m.stride[0], _lib.ptr(self._wgrad_scratch(m, a_in)),
-                                                 _lib.ptr(m.weight.grad), side_stream.cuda_stream))
-                else:
+                                                 _lib.ptr(m.weight.grad), _lib.ptr(m.bias.grad), side_stream.cuda_stream))
+                else:   # bias first (it only needs g), then the library's weight gradient
+                    _lib.check(lib.rb_bias_grad(_lib.ptr(g), g.shape[0], g.shape[1], g.shape[2] * g.shape[3],
+                                                _lib.ptr(m.bias.grad), side_stream.cuda_stream))
                     _, gw, _ = torch.ops.aten.convolution_backward(g, a_in, m.weight, None, m.stride, m.padding, m.dilation, False,
                                                                    [0, 0], m.groups, [False, True, False])
                     m.weight.grad.copy_(gw)

@@ -586,13 +586,16 @@ def test_conv_wgrad_first_layer(B, IC, IH, OC, K, S):
     assert n > 0
     scratch = torch.empty(n, device=DEV)
     out = torch.full((OC, IC, K, K), 7.0, device=DEV)                  # must be overwritten
+    bias = torch.full((OC,), 7.0, device=DEV)
     _lib.check(L.rb_conv_wgrad(g.data_ptr(), x.data_ptr(), B, IC, IH, IH, OC, K, S, scratch.data_ptr(), out.data_ptr(),
-                               torch.cuda.current_stream().cuda_stream))
+                               bias.data_ptr(), torch.cuda.current_stream().cuda_stream))
     scale = float(ref.abs().max())
     np.testing.assert_allclose(cpu(out), cpu(ref), rtol=0, atol=2e-6 * scale)
+    bref = g.double().sum((0, 2, 3))
+    np.testing.assert_allclose(cpu(bias), cpu(bref), rtol=0, atol=2e-6 * float(bref.abs().max()))
     out2 = torch.empty_like(out)
     _lib.check(L.rb_conv_wgrad(g.data_ptr(), x.data_ptr(), B, IC, IH, IH, OC, K, S, scratch.data_ptr(), out2.data_ptr(),
-                               torch.cuda.current_stream().cuda_stream))
+                               None, torch.cuda.current_stream().cuda_stream))
     assert torch.equal(out, out2)
 
 
