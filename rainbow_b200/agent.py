@@ -437,7 +437,8 @@ class Agent:
                             self.sync.all_reduce_(self.optimiser.flat_grad[self.optimiser.conv_end:])
                         head_reduced = torch.cuda.Event()
                         head_reduced.record(s_tg)
-                grads_done = on.conv_backward_into_grads(acts, dx.view_as(acts[-1]), s_ns)
+                grads_done = on.conv_backward_into_grads(acts, dx.view_as(acts[-1]), s_ns,
+                                                         first_layer_stream=None if self.sync.enabled else s_tg)
                 main.wait_event(grads_done)
                 if self.sync.enabled:
                     self.sync.all_reduce_(self.optimiser.flat_grad[:self.optimiser.conv_end])

@@ -334,14 +334,16 @@ k_tree_sample(const float* __restrict__ tree, int64_t tree_start, int64_t size, 
   const int64_t len = tree_start + size;
   const int L = tree_depth(tree_start);
   if (tid == 0) s_valid = 1;
+  // every scalar the kernel needs is requested before the staging barrier, so these round trips overlap the staging loads
+  const int64_t head = ring_state[0];
+  const bool full = ring_state[1] != 0;
+  const unsigned long long ctr0 = (u01 == nullptr) ? *rng_counter : 0ull;
+  const float b = beta_dev ? *beta_dev : beta;
   stage_top(tree, s_top, len);
 
   const float p_total = s_top[0];                          // memory.py:149
   const float seg = __fdiv_rn(p_total, (float)B);          // memory.py:125 (float32)
   const double segd = (double)seg;
-  const int64_t head = ring_state[0];
-  const bool full = ring_state[1] != 0;
-  const unsigned long long ctr0 = (u01 == nullptr) ? *rng_counter : 0ull;
   const int tries = (u01 != nullptr) ? u01_attempts : max_attempts;
 
   int attempt = 0;
@@ -380,7 +382,6 @@ k_tree_sample(const float* __restrict__ tree, int64_t tree_start, int64_t size, 
   }
 
   // importance-sampling weights (memory.py:151-154), float32 like numpy
-  const float b = beta_dev ? *beta_dev : beta;
   const float nb = -b;
   const float count = (float)(full ? size : head);
   float wmax = -CUDART_INF_F;
