@@ -505,126 +505,78 @@ k_head_wgrad2(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGr
 
 // Layer-2 backward, input gradient with the ReLU mask of layer 1 folded in:
 // dh[m][s*H + k] = (h > 0) * sum_o dz[m][col(o)] * W2_s[o][k].   B <= 32 rows.
-// grid = (H/32, 2 streams x 4 row ranges), launched as 4-CTA clusters: each CTA fetches its [rows x 32] slab of mu and
-// sigma with ONE batch of cp.async (all loads in flight at once: a single memory latency), stages its dz slice
-// transposed, composes W2 in place, and the four partial tiles are summed over distributed shared memory.
-constexpr int DH_K = 32;
-constexpr int DH_LD = DH_K + 4;
+// The layer is tiny (1.5 MB of weights) and sits on the critical path between the loss and the layer-1 backward, so the
+// kernel is organised around ONE memory round trip: grid = 2 streams x H/8 CTAs; a CTA stages the stream's whole dz block
+// [32][Ns] and its 8-column slab of W2 (mu and sigma rows, 32 contiguous bytes each) with cp.async, all in flight at once,
+// composes the noisy weights in place, and thread (m, k) runs one Ns-long dot product out of shared memory.
+// Writes dh [B][2H] and its transpose dhT [2H][32] (rows past B zero) for k_head_bwd1.
+constexpr int DH_KB = 8;    // hidden units per CTA
+constexpr int DH_T = 256;   // 32 batch rows x 8 hidden units
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
 }
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem));
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
 
-constexpr int DH_SPLIT = 4;  // CTAs per cluster: the stream's rows of W2 are split four ways
-
-__global__ void __cluster_dims__(1, DH_SPLIT, 1) __launch_bounds__(HT)
+__global__ void __launch_bounds__(DH_T)
 k_head_dh(const __grid_constant__ HeadDesc d, const float* __restrict__ dz, const float* __restrict__ h, int B,
-          float* __restrict__ dh, float* __restrict__ dhT, int rows_pad) {
+          float* __restrict__ dh, float* __restrict__ dhT, int ld_dz) {
   extern __shared__ __align__(16) float smem_dh[];
-  float* Wm = smem_dh;                           // [rows_pad][DH_LD] raw mu, composed in place
-  float* Wsg = Wm + (size_t)rows_pad * DH_LD;    // [rows_pad][DH_LD] raw sigma
-  float* Dt = Wsg + (size_t)rows_pad * DH_LD;    // [rows_pad][36]    dz transposed [o][m]
-  __shared__ __align__(16) float Red[32][DH_LD]; // partial tile handed over the cluster
-  cg::cluster_group cluster = cg::this_cluster();
-  const int tid = threadIdx.x, tk = tid & 7, tm = tid >> 3;  // micro tile: 2 rows (m) x 4 k
-  const int s = blockIdx.y / DH_SPLIT, q = blockIdx.y % DH_SPLIT, k0 = blockIdx.x * DH_K;
-  const int Ns = n2_of(d, s), colbase = col2_of(d, s), ncols = d.Z + d.A * d.Z;
-  const int per = (Ns + DH_SPLIT - 1) / DH_SPLIT;
-  const int ob = q * per, nb = max(0, min(per, Ns - ob));   // this CTA's rows [ob, ob + nb)
+  const int s = blockIdx.y, k0 = blockIdx.x * DH_KB;
+  const int Ns = n2_of(d, s), colbase = col2_of(d, s), ncols = d.Z + d.A * d.Z, H = d.H;
+  float* Dz = smem_dh;                                  // [32][ld_dz]   dz block of this stream
+  float* Wm = Dz + 32 * ld_dz;                          // [Ns][DH_KB]   mu slab, composed in place
+  float* Wsg = Wm + (size_t)((Ns + 3) & ~3) * DH_KB;    // [Ns][DH_KB]   sigma slab
+  const int tid = threadIdx.x;
   const float* ei = d.ei2[s];
   const float* eo = d.eo2[s];
-  float acc[2][4];
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-  // the whole slab in one batch of cp.async: a single memory latency
-  for (int idx = tid; idx < nb * (DH_K / 4); idx += HT) {
-    const int o = idx >> 3, k4 = (idx & 7) * 4;
-    cp_async16(Wm + (size_t)o * DH_LD + k4, d.w2_mu[s] + (size_t)(ob + o) * d.H + k0 + k4);
-    if (ei) cp_async16(Wsg + (size_t)o * DH_LD + k4, d.w2_sig[s] + (size_t)(ob + o) * d.H + k0 + k4);
+  // dz rows start at arbitrary 4-byte offsets (colbase = Z for the advantage stream): 4-byte cp.async
+  for (int idx = tid; idx < B * Ns; idx += DH_T) {
+    const int m = idx / Ns, o = idx - m * Ns;
+    cp_async4(Dz + m * ld_dz + o, dz + (size_t)m * ncols + colbase + o);
   }
-  for (int base = tid; base < 32 * nb; base += HT * 8) {  // dz slice, transposed; 8 loads in flight per thread
-    float v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int idx = base + u * HT;
-      v[u] = 0.0f;
-      if (idx < 32 * nb) {
-        const int m = idx / nb, o = idx - m * nb;
-        if (m < B) v[u] = __ldg(dz + (size_t)m * ncols + colbase + ob + o);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int idx = base + u * HT;
-      if (idx < 32 * nb) {
-        const int m = idx / nb, o = idx - m * nb;
-        Dt[(size_t)o * 36 + m] = v[u];
-      }
-    }
+  for (int idx = tid; idx < Ns * 2; idx += DH_T) {      // two 16-byte chunks per weight row and tensor
+    const int o = idx >> 1, c = (idx & 1) * 4;
+    cp_async16(Wm + o * DH_KB + c, d.w2_mu[s] + (size_t)o * H + k0 + c);
+    if (ei) cp_async16(Wsg + o * DH_KB + c, d.w2_sig[s] + (size_t)o * H + k0 + c);
   }
+  const int m = tid >> 3, k = tid & 7;
+  const float hv = (m < B) ? __ldg(h + (size_t)m * (2 * H) + s * H + k0 + k) : 0.0f;
   cp_async_wait_all();
   __syncthreads();
-  if (ei) {  // compose W2 = mu + sigma * (eps_out[o] * eps_in[k]) in place (one vectorised pass, all threads)
-    for (int idx = tid; idx < nb * (DH_K / 4); idx += HT) {
-      const int o = idx >> 3, k4 = (idx & 7) * 4;
-      float4 w = *reinterpret_cast<const float4*>(Wm + (size_t)o * DH_LD + k4);
-      const float4 sg = *reinterpret_cast<const float4*>(Wsg + (size_t)o * DH_LD + k4);
-      const float4 ek = __ldg(reinterpret_cast<const float4*>(ei + k0 + k4));
-      const float e = __ldg(eo + ob + o);
+  if (ei) {  // W2 = mu + sigma * (eps_out[o] * eps_in[k]) in place
+    for (int idx = tid; idx < Ns * 2; idx += DH_T) {
+      const int o = idx >> 1, c = (idx & 1) * 4;
+      float4 w = *reinterpret_cast<const float4*>(Wm + o * DH_KB + c);
+      const float4 sg = *reinterpret_cast<const float4*>(Wsg + o * DH_KB + c);
+      const float4 ek = __ldg(reinterpret_cast<const float4*>(ei + k0 + c));
+      const float e = __ldg(eo + o);
       w.x = fmaf(sg.x, e * ek.x, w.x); w.y = fmaf(sg.y, e * ek.y, w.y);
       w.z = fmaf(sg.z, e * ek.z, w.z); w.w = fmaf(sg.w, e * ek.w, w.w);
-      *reinterpret_cast<float4*>(Wm + (size_t)o * DH_LD + k4) = w;
+      *reinterpret_cast<float4*>(Wm + o * DH_KB + c) = w;
     }
     __syncthreads();
   }
-#pragma unroll 8
-  for (int o = 0; o < nb; ++o) {
-    const float4 w = *reinterpret_cast<const float4*>(Wm + (size_t)o * DH_LD + tk * 4);
-    const float2 a = *reinterpret_cast<const float2*>(Dt + (size_t)o * 36 + tm * 2);
-    acc[0][0] = fmaf(a.x, w.x, acc[0][0]); acc[0][1] = fmaf(a.x, w.y, acc[0][1]);
-    acc[0][2] = fmaf(a.x, w.z, acc[0][2]); acc[0][3] = fmaf(a.x, w.w, acc[0][3]);
-    acc[1][0] = fmaf(a.y, w.x, acc[1][0]); acc[1][1] = fmaf(a.y, w.y, acc[1][1]);
-    acc[1][2] = fmaf(a.y, w.z, acc[1][2]); acc[1][3] = fmaf(a.y, w.w, acc[1][3]);
-  }
-  // ---- sum the four row-range partials in fixed rank order over distributed shared memory ----
-  const unsigned rank = cluster.block_rank();
-  if (rank != 0) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-      *reinterpret_cast<float4*>(&Red[tm * 2 + i][tk * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-  }
-  cluster.sync();
-  if (rank == 0) {
-#pragma unroll
-    for (int r = 1; r < DH_SPLIT; ++r) {
-      const float* remote = cluster.map_shared_rank(&Red[0][0], r);
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const float4 v = *reinterpret_cast<const float4*>(remote + (tm * 2 + i) * DH_LD + tk * 4);
-        acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
-      }
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (m < B) {
+    const float* dr = Dz + m * ld_dz;
+    int o = 0;
+    for (; o + 3 < Ns; o += 4) {
+      a0 = fmaf(dr[o], Wm[o * DH_KB + k], a0);
+      a1 = fmaf(dr[o + 1], Wm[(o + 1) * DH_KB + k], a1);
+      a2 = fmaf(dr[o + 2], Wm[(o + 2) * DH_KB + k], a2);
+      a3 = fmaf(dr[o + 3], Wm[(o + 3) * DH_KB + k], a3);
     }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int m = tm * 2 + i;
-      float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < B) {
-        const size_t off = (size_t)m * (2 * d.H) + s * d.H + k0 + tk * 4;
-        const float4 hv = __ldg(reinterpret_cast<const float4*>(h + off));
-        o4.x = hv.x > 0.f ? acc[i][0] : 0.f; o4.y = hv.y > 0.f ? acc[i][1] : 0.f;
-        o4.z = hv.z > 0.f ? acc[i][2] : 0.f; o4.w = hv.w > 0.f ? acc[i][3] : 0.f;
-        *reinterpret_cast<float4*>(dh + off) = o4;
-      }
-      // transposed copy [2H][32] (rows past B are zero) for the layer-1 kernel's input-gradient half
-      float* t = dhT + (size_t)(s * d.H + k0 + tk * 4) * 32 + m;
-      t[0] = o4.x; t[32] = o4.y; t[64] = o4.z; t[96] = o4.w;
-    }
+    for (; o < Ns; ++o) a0 = fmaf(dr[o], Wm[o * DH_KB + k], a0);
   }
-  cluster.sync();  // remote shared memory must outlive the reads above
+  const float v = (m < B && hv > 0.f) ? ((a0 + a1) + (a2 + a3)) : 0.0f;
+  if (m < B) dh[(size_t)m * (2 * H) + s * H + k0 + k] = v;
+  dhT[(size_t)(s * H + k0 + k) * 32 + m] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -634,7 +586,9 @@ k_head_dh(const __grid_constant__ HeadDesc d, const float* __restrict__ dz, cons
 // grid = (K1/32, 2 streams x 2 halves of the stream's rows) launched as clusters of 4 CTAs along y: three CTAs
 // hand their dx partial to rank 0 through distributed shared memory (fixed rank order -> deterministic).
 // 256 threads: warps 0-3 compute the weight-gradient tile of the current 32-row chunk of W1 while warps
-// 4-7 accumulate the input gradient from the same staged tiles.  The chunks (raw mu / sigma rows, the dh chunk in both
+// 4-7 accumulate the input gradient from the same staged tiles, both as error-compensated TF32 products on the warp-level
+// tensor-core path (mma.sync.m16n8k8, three MMAs per product: fp32-equivalent results) -- the FFMA version of this kernel
+// was instruction-issue bound (12.2 M warp instructions, FMA pipe 30 % busy: r02b ncu).  The chunks (raw mu / sigma rows, the dh chunk in both
 // orientations -- k_head_dh writes dh [m][2H] and its transpose dhT [2H][32], so nothing is transposed through shared
 // memory here) arrive through a 3-stage cp.async ring, two chunks ahead of the one being consumed: the eight dependent
 // memory latencies of the old single-stage register prefetch collapse into one plus streaming.
@@ -644,19 +598,49 @@ constexpr int B1_O = 32;   // rows of W1 per chunk
 constexpr int B1_T = 256;  // threads
 
 constexpr int B1_STAGES = 3;                 // cp.async ring: two chunks in flight ahead of the one being consumed (3 CTAs per SM: one wave)
-constexpr int B1_LD = B1_K + 4;              // row stride of every staged tile (floats): 144 B, keeps 16-byte alignment
-constexpr int B1_STAGE = 4 * 32 * B1_LD;     // floats per stage: W mu (composed in place) | W sigma | dh [m][o] | dhT [o][m]
+// Row strides (floats) chosen for the mma.m16n8k8 fragment loads: "A" tiles (rows indexed by lane / 4, columns by lane % 4)
+// want a stride = 4 (mod 32), "B" tiles (rows by lane % 4, columns by lane / 4) a stride = 8 (mod 32): both conflict free.
+constexpr int B1_LDW = B1_K + 8;             // W mu / sigma chunks [o][k]   (B operand of the dx product)
+constexpr int B1_LDD = B1_K + 4;             // dh chunks [m][o] and [o][m]  (A operands)
+constexpr int B1_STAGE = 2 * 32 * B1_LDW + 2 * 32 * B1_LDD;   // floats per stage: W mu (composed in place) | W sigma | dh | dhT
+
+// ---- error-compensated TF32 on the warp-level tensor-core path (mma.sync.m16n8k8): fp32-equivalent products -------------
+// hi = the value with its low 13 mantissa bits cleared (a TF32 number), lo = value - hi (exact);
+// D += Alo*Bhi + Ahi*Blo + Ahi*Bhi, fp32 accumulation (the dropped lo*lo term is 2^-22 relative).
+__device__ __forceinline__ void tf32_split(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v) & 0xFFFFE000u;
+  lo = __float_as_uint(__fsub_rn(v, __uint_as_float(hi)));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// one 16 x 8 output block, K = 8: A block at `a` (row stride lda, rows = M index, columns = K index), B fragments given
+__device__ __forceinline__ void mma3_block(float (&c)[4], const float* a, int lda, const uint32_t (&bhi)[2], const uint32_t (&blo)[2],
+                                           int gid, int tig) {
+  uint32_t ahi[4], alo[4];
+  tf32_split(a[gid * lda + tig], ahi[0], alo[0]);
+  tf32_split(a[(gid + 8) * lda + tig], ahi[1], alo[1]);
+  tf32_split(a[gid * lda + tig + 4], ahi[2], alo[2]);
+  tf32_split(a[(gid + 8) * lda + tig + 4], ahi[3], alo[3]);
+  mma_tf32(c, alo, bhi);
+  mma_tf32(c, ahi, blo);
+  mma_tf32(c, ahi, bhi);
+}
 
 __global__ void __cluster_dims__(1, 4, 1) __launch_bounds__(B1_T)
 k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrads g, const float* __restrict__ x,
             const float* __restrict__ dh, const float* __restrict__ dhT, int B, float* __restrict__ dx, int relu_mask_x) {
   extern __shared__ __align__(16) float b1_ring[];     // [B1_STAGES][B1_STAGE]
-  __shared__ __align__(16) float Xs[32][B1_K + 4];    // x slice [m][k]
+  __shared__ __align__(16) float Xs[32][B1_K + 8];    // x slice [m][k]  (B operand of the weight-gradient product)
   __shared__ __align__(16) float Red[32][B1_K + 4];   // dx partial handed over the cluster
   __shared__ float Eo[B1_STAGES][B1_O];               // eps_out of the staged chunks' rows
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x;
-  const int role = tid >> 7, rt = tid & 127, tk = rt & 15, to = rt >> 4;  // micro tile: 4 rows (o or m) x 2 k
+  // warps 0-3: weight-gradient tile [32 o][32 k] of the current chunk; warps 4-7: input gradient [32 m][32 k].  Warp w of a
+  // role owns the 8 columns n0 = 8 w of its role's tile, both 16-row blocks (mma.m16n8k8 fragments: gid = lane / 4, tig = lane % 4)
+  const int role = tid >> 7, rt = tid & 127, lane = tid & 31, gid = lane >> 2, tig = lane & 3, n0 = ((tid >> 5) & 3) * 8;
   // cluster of 4 CTAs along y: (stream, half of the stream's W1 rows); rank 0 sums the four dx partials
   const int s = blockIdx.y >> 1, half = blockIdx.y & 1, k0 = blockIdx.x * B1_K, K = d.K1, H = d.H;
   const int o_begin = half * (H / 2), n_chunks = (H / 2) / B1_O;
@@ -667,17 +651,17 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
   const int st_r = tid >> 3, st_c = (tid & 7) * 4;   // staging coordinates: one 16-byte chunk of each of the four tiles
 
   auto Wm = [&](int st) { return b1_ring + (size_t)st * B1_STAGE; };
-  auto Wsg = [&](int st) { return b1_ring + (size_t)st * B1_STAGE + 32 * B1_LD; };
-  auto Dm = [&](int st) { return b1_ring + (size_t)st * B1_STAGE + 2 * 32 * B1_LD; };   // dh chunk [m][o]
-  auto Dt = [&](int st) { return b1_ring + (size_t)st * B1_STAGE + 3 * 32 * B1_LD; };   // dh chunk [o][m]
+  auto Wsg = [&](int st) { return b1_ring + (size_t)st * B1_STAGE + 32 * B1_LDW; };
+  auto Dm = [&](int st) { return b1_ring + (size_t)st * B1_STAGE + 2 * 32 * B1_LDW; };                 // dh chunk [m][o]
+  auto Dt = [&](int st) { return b1_ring + (size_t)st * B1_STAGE + 2 * 32 * B1_LDW + 32 * B1_LDD; };   // dh chunk [o][m]
   auto issue = [&](int c) {   // chunk c of this CTA's rows -> stage c % B1_STAGES (always commits, possibly an empty group)
     if (c < n_chunks) {
       const int st = c % B1_STAGES, ob = o_begin + c * B1_O;
-      cp_async16_zfill(Wm(st) + st_r * B1_LD + st_c, mu + (size_t)(ob + st_r) * K + k0 + st_c, true);
-      if (ei) cp_async16_zfill(Wsg(st) + st_r * B1_LD + st_c, sg + (size_t)(ob + st_r) * K + k0 + st_c, true);
+      cp_async16_zfill(Wm(st) + st_r * B1_LDW + st_c, mu + (size_t)(ob + st_r) * K + k0 + st_c, true);
+      if (ei) cp_async16_zfill(Wsg(st) + st_r * B1_LDW + st_c, sg + (size_t)(ob + st_r) * K + k0 + st_c, true);
       const bool row_ok = st_r < B;
-      cp_async16_zfill(Dm(st) + st_r * B1_LD + st_c, row_ok ? dh + (size_t)st_r * (2 * H) + s * H + ob + st_c : dh, row_ok);
-      cp_async16_zfill(Dt(st) + st_r * B1_LD + st_c, dhT + (size_t)(s * H + ob + st_r) * 32 + st_c, true);
+      cp_async16_zfill(Dm(st) + st_r * B1_LDD + st_c, row_ok ? dh + (size_t)st_r * (2 * H) + s * H + ob + st_c : dh, row_ok);
+      cp_async16_zfill(Dt(st) + st_r * B1_LDD + st_c, dhT + (size_t)(s * H + ob + st_r) * 32 + st_c, true);
       if (st_c == 0) Eo[st][st_r] = eo ? __ldg(eo + ob + st_r) : 0.0f;
     }
     cp_async_commit();
@@ -691,13 +675,25 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
     if (m < B) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)m * K + k0 + kk));
     *reinterpret_cast<float4*>(&Xs[m][kk]) = v;
   }
-  const float ei0 = ei ? __ldg(ei + k0 + tk * 2) : 0.0f, ei1v = ei ? __ldg(ei + k0 + tk * 2 + 1) : 0.0f;
+  const float ei0 = ei ? __ldg(ei + k0 + n0 + 2 * tig) : 0.0f, ei1v = ei ? __ldg(ei + k0 + n0 + 2 * tig + 1) : 0.0f;
   float4 e4s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ei) e4s = __ldg(reinterpret_cast<const float4*>(ei + k0 + st_c));
 
-  float acc[4][2];
+  float acc[2][4];   // input-gradient accumulators (mma C fragments of the two 16-row blocks), kept across the chunks
 #pragma unroll
-  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0f;
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  __syncthreads();   // Xs is complete
+  // the weight-gradient product's B operand (x slice, K index = batch row) never changes: fragments split once
+  uint32_t xhi[4][2], xlo[4][2];
+  if (role == 0) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      tf32_split(Xs[8 * ks + tig][n0 + gid], xhi[ks][0], xlo[ks][0]);
+      tf32_split(Xs[8 * ks + tig + 4][n0 + gid], xhi[ks][1], xlo[ks][1]);
+    }
+  }
 
   for (int c = 0; c < n_chunks; ++c) {
     const int st = c % B1_STAGES, ob = o_begin + c * B1_O;
@@ -705,55 +701,50 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
     __syncthreads();                  // ... and everybody else's; everybody is also done with chunk c - 1
     issue(c + B1_STAGES - 1);         // overwrites the stage chunk c - 1 used
     if (ei) {                         // W = mu + sigma * (eps_out[o] * eps_in[k]) in place   (model.py:39,43)
-      float4 w = *reinterpret_cast<const float4*>(Wm(st) + st_r * B1_LD + st_c);
-      const float4 sg4 = *reinterpret_cast<const float4*>(Wsg(st) + st_r * B1_LD + st_c);
+      float4 w = *reinterpret_cast<const float4*>(Wm(st) + st_r * B1_LDW + st_c);
+      const float4 sg4 = *reinterpret_cast<const float4*>(Wsg(st) + st_r * B1_LDW + st_c);
       const float e = Eo[st][st_r];
       w.x = fmaf(sg4.x, e * e4s.x, w.x); w.y = fmaf(sg4.y, e * e4s.y, w.y);
       w.z = fmaf(sg4.z, e * e4s.z, w.z); w.w = fmaf(sg4.w, e * e4s.w, w.w);
-      *reinterpret_cast<float4*>(Wm(st) + st_r * B1_LD + st_c) = w;
+      *reinterpret_cast<float4*>(Wm(st) + st_r * B1_LDW + st_c) = w;
       __syncthreads();
     }
     if (role == 0) {
-      // ---- weight gradient tile [32 o][32 k]: reduction over the batch rows ----
-      const float* Ds = Dm(st);
-      float ga[4][2];
+      // ---- weight gradient tile [32 o][32 k] = dhT chunk [o][m] x x slice [m][k]: reduction over the batch rows ----
+      const float* DsT = Dt(st);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) ga[i][0] = ga[i][1] = 0.0f;
-#pragma unroll 8
-      for (int m = 0; m < 32; ++m) {
-        const float4 a = *reinterpret_cast<const float4*>(Ds + m * B1_LD + to * 4);
-        const float2 b = *reinterpret_cast<const float2*>(&Xs[m][tk * 2]);
-        ga[0][0] = fmaf(a.x, b.x, ga[0][0]); ga[0][1] = fmaf(a.x, b.y, ga[0][1]);
-        ga[1][0] = fmaf(a.y, b.x, ga[1][0]); ga[1][1] = fmaf(a.y, b.y, ga[1][1]);
-        ga[2][0] = fmaf(a.z, b.x, ga[2][0]); ga[2][1] = fmaf(a.z, b.y, ga[2][1]);
-        ga[3][0] = fmaf(a.w, b.x, ga[3][0]); ga[3][1] = fmaf(a.w, b.y, ga[3][1]);
-      }
+      for (int mb = 0; mb < 2; ++mb) {
+        float ga[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int o = ob + to * 4 + i;
-        const size_t off = (size_t)o * K + k0 + tk * 2;
-        __stcs(reinterpret_cast<float2*>(g.w1_mu[s] + off), make_float2(ga[i][0], ga[i][1]));
-        const float e = Eo[st][to * 4 + i];
-        __stcs(reinterpret_cast<float2*>(g.w1_sig[s] + off), make_float2(ga[i][0] * (e * ei0), ga[i][1] * (e * ei1v)));
+        for (int ks = 0; ks < 4; ++ks) mma3_block(ga, DsT + (16 * mb) * B1_LDD + 8 * ks, B1_LDD, xhi[ks], xlo[ks], gid, tig);
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {   // C fragment: rows gid and gid + 8, columns 2 tig and 2 tig + 1
+          const int ol = 16 * mb + gid + 8 * hrow;
+          const size_t off = (size_t)(ob + ol) * K + k0 + n0 + 2 * tig;
+          const float g0 = ga[2 * hrow], g1 = ga[2 * hrow + 1];
+          __stcs(reinterpret_cast<float2*>(g.w1_mu[s] + off), make_float2(g0, g1));
+          const float e = Eo[st][ol];
+          __stcs(reinterpret_cast<float2*>(g.w1_sig[s] + off), make_float2(g0 * (e * ei0), g1 * (e * ei1v)));
+        }
       }
       if (blockIdx.x == 0 && rt < B1_O) {  // bias gradients of this chunk's rows
+        const float* Ds = Dm(st);
         float bs = 0.0f;
-        for (int m = 0; m < 32; ++m) bs += Ds[m * B1_LD + rt];
+        for (int m = 0; m < 32; ++m) bs += Ds[m * B1_LDD + rt];
         g.b1_mu[s][ob + rt] = bs;
         g.b1_sig[s][ob + rt] = bs * Eo[st][rt];
       }
     } else {
-      // ---- input gradient [32 m][32 k]: reduction over this chunk's rows of W1 ----
-      const float* DsT = Dt(st);
+      // ---- input gradient [32 m][32 k] += dh chunk [m][o] x composed W chunk [o][k]: reduction over the chunk's rows ----
+      const float* Ds = Dm(st);
       const float* Ws = Wm(st);
-#pragma unroll 8
-      for (int oo = 0; oo < B1_O; ++oo) {
-        const float4 a = *reinterpret_cast<const float4*>(DsT + oo * B1_LD + to * 4);
-        const float2 b = *reinterpret_cast<const float2*>(Ws + oo * B1_LD + tk * 2);
-        acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
-        acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
-        acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]);
-        acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t whi[2], wlo[2];
+        tf32_split(Ws[(8 * ks + tig) * B1_LDW + n0 + gid], whi[0], wlo[0]);
+        tf32_split(Ws[(8 * ks + tig + 4) * B1_LDW + n0 + gid], whi[1], wlo[1]);
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) mma3_block(acc[mb], Ds + (16 * mb) * B1_LDD + 8 * ks, B1_LDD, whi, wlo, gid, tig);
       }
     }
   }
@@ -762,7 +753,10 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
   const unsigned rank = cluster.block_rank();
   if (rank != 0 && role == 1) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) *reinterpret_cast<float2*>(&Red[to * 4 + i][tk * 2]) = make_float2(acc[i][0], acc[i][1]);
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow)
+        *reinterpret_cast<float2*>(&Red[16 * mb + gid + 8 * hrow][n0 + 2 * tig]) = make_float2(acc[mb][2 * hrow], acc[mb][2 * hrow + 1]);
   }
   cluster.sync();
   if (rank == 0 && role == 1) {
@@ -770,25 +764,29 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
     for (int r = 1; r < 4; ++r) {
       const float* remote = cluster.map_shared_rank(&Red[0][0], r);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 v = *reinterpret_cast<const float2*>(remote + (to * 4 + i) * (B1_K + 4) + tk * 2);
-        acc[i][0] += v.x;
-        acc[i][1] += v.y;
-      }
+      for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int hrow = 0; hrow < 2; ++hrow) {
+          const float2 v = *reinterpret_cast<const float2*>(remote + (16 * mb + gid + 8 * hrow) * (B1_K + 4) + n0 + 2 * tig);
+          acc[mb][2 * hrow] += v.x;
+          acc[mb][2 * hrow + 1] += v.y;
+        }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int m = to * 4 + i;
-      if (m < B) {
-        float2 o2 = make_float2(acc[i][0], acc[i][1]);
-        if (relu_mask_x) {  // x = relu(conv output): fold that ReLU's backward in (x > 0 <=> pre-activation > 0)
-          const float2 xv = *reinterpret_cast<const float2*>(&Xs[m][tk * 2]);
-          o2.x = xv.x > 0.f ? o2.x : 0.f;
-          o2.y = xv.y > 0.f ? o2.y : 0.f;
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const int m = 16 * mb + gid + 8 * hrow;
+        if (m < B) {
+          float2 o2 = make_float2(acc[mb][2 * hrow], acc[mb][2 * hrow + 1]);
+          if (relu_mask_x) {  // x = relu(conv output): fold that ReLU's backward in (x > 0 <=> pre-activation > 0)
+            const float2 xv = *reinterpret_cast<const float2*>(&Xs[m][n0 + 2 * tig]);
+            o2.x = xv.x > 0.f ? o2.x : 0.f;
+            o2.y = xv.y > 0.f ? o2.y : 0.f;
+          }
+          *reinterpret_cast<float2*>(dx + (size_t)m * K + k0 + n0 + 2 * tig) = o2;
         }
-        *reinterpret_cast<float2*>(dx + (size_t)m * K + k0 + tk * 2) = o2;
       }
-    }
   }
   cluster.sync();  // remote shared memory must outlive the reads above
 }
@@ -1121,14 +1119,14 @@ int rb_head_backward(const rb_head_params* p, const rb_head_grads* gr, const flo
   if (rc != RB_OK) return rc;
   if (parts & RB_HEAD_BWD_DH) {
     const int ns_max = d.A * d.Z > d.Z ? d.A * d.Z : d.Z;
-    const int rows_pad = (((ns_max + DH_SPLIT - 1) / DH_SPLIT) + 3) & ~3;
-    const size_t smem = (size_t)rows_pad * (2 * DH_LD + 36) * sizeof(float);
-    if (smem > 200 * 1024) return rbi::fail(RB_ERR_RANGE, "rb_head_backward: actions * atoms too large for the dh kernel");
+    const int ld_dz = ns_max | 1;                       // odd row stride: the 32 rows of a column hit 32 different banks
+    const size_t smem = ((size_t)32 * ld_dz + 2 * (size_t)((ns_max + 3) & ~3) * DH_KB) * sizeof(float);
+    if (smem > 200 * 1024 || d.H % DH_KB) return rbi::fail(RB_ERR_RANGE, "rb_head_backward: actions * atoms too large for the dh kernel");
     rc = rbi::ensure_dynamic_smem(k_head_dh, smem, "rb_head_backward");
     if (rc != RB_OK) return rc;
-    dim3 grid(d.H / DH_K, 2 * DH_SPLIT);
+    dim3 grid(d.H / DH_KB, 2);
     rbi::ProfScope prof_(RB_K_HEAD_DH, st);
-    k_head_dh<<<grid, HT, smem, st>>>(d, dz, h, B, dh_scratch, dh_scratch + (size_t)B * 2 * d.H, rows_pad);
+    k_head_dh<<<grid, DH_T, smem, st>>>(d, dz, h, B, dh_scratch, dh_scratch + (size_t)B * 2 * d.H, ld_dz);
   }
   rc = rbi::check_launch("rb_head_backward(dh)");
   if (rc != RB_OK) return rc;

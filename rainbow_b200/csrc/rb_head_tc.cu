@@ -79,6 +79,9 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {   // pull a box into L2 only
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -184,6 +187,12 @@ k_head_fc1_tc(const __grid_constant__ CUtensorMap tm_mu0, const __grid_constant_
       if (noisy) tma_prefetch_desc(sg_map);
       tma_prefetch_desc(&tm_xlo);
       const uint32_t bytes = TC_W_BYTES * (noisy ? 2 : 1) + X_BYTES;
+      // the weight tiles beyond the ring's depth start their trip from HBM to L2 now, so that when a stage frees up its
+      // reload is an L2 hit instead of a second exposed DRAM latency
+      for (int i = TC_STAGES; i < nkt; ++i) {
+        tma_prefetch_l2_2d(mu_map, (kt_begin + i) * TC_BK, n0);
+        if (noisy) tma_prefetch_l2_2d(sg_map, (kt_begin + i) * TC_BK, n0);
+      }
       for (int i = 0; i < nkt; ++i) {
         const int st = i % TC_STAGES, round = i / TC_STAGES;
         if (i >= TC_STAGES) mbar_wait(empty + st, (round - 1) & 1);
