@@ -202,6 +202,13 @@ int ctas_for(int64_t part) {
   int64_t want = (part / 4 + PEER_THREADS - 1) / PEER_THREADS;
   return (int)(want < 1 ? 1 : (want > PEER_MAX_CTAS ? PEER_MAX_CTAS : want));
 }
+// The reduce-scatter runs BESIDE the conv backward (whose library kernels need free SM slots to start): one CTA per SM is
+// enough to keep NVLink busy (eight 16-byte peer loads in flight per thread) and leaves room for them (a 592-CTA launch
+// filled every register file and delayed the concurrent dgrad by 30 us at N = 2, mgpu_2 timeline).
+int reduce_ctas_for(int64_t part) {
+  const int c = ctas_for(part);
+  return c > 148 ? 148 : c;
+}
 
 // scratch layout: per segment PEER_MAX_CTAS doubles of CTA partials, then double seg_norm[PEER_SEGS], then tickets
 double* scratch_partials(void* scratch, int seg) { return reinterpret_cast<double*>(scratch) + (size_t)seg * PEER_MAX_CTAS; }
@@ -225,7 +232,7 @@ int rb_peer_reduce(const float* const* peer_grad, uint64_t* const* peer_flags, i
   if (seg_begin < 0 || seg_len <= 0 || seg_len % (4 * (int64_t)world) || seg_begin % 4)
     return rbi::fail(RB_ERR_INVAL, "rb_peer_reduce: segment must start on a multiple of 4 and hold a multiple of 4 * world elements");
   const int64_t part = seg_len / world;
-  k_peer_reduce<<<ctas_for(part), PEER_THREADS, 0, (cudaStream_t)stream>>>(pb, epoch, seg, seg_begin, part, grad_scale, gred_part,
+  k_peer_reduce<<<reduce_ctas_for(part), PEER_THREADS, 0, (cudaStream_t)stream>>>(pb, epoch, seg, seg_begin, part, grad_scale, gred_part,
                                                                          scratch_partials(scratch, seg),
                                                                          scratch_tickets(scratch) + seg, scratch_seg_norm(scratch));
   return rbi::check_launch("rb_peer_reduce");

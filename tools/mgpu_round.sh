@@ -19,8 +19,8 @@ run() {  # name, timeout, env..., -- script args
 run peer_check 200 RB_X=1 -- tools/peer_adam_check.py
 run bench_nccl 400 RB_X=1 -- bench.py --gpus $N --steps 300 --warmup 10
 run bench_peer 400 RB_X=1 -- bench.py --gpus $N --steps 300 --warmup 10 --peer-optimizer
-run timeline_nccl 300 RB_X=1 -- tools/timeline.py --cap 100000 --out $OUT/timeline_nccl.json
-run timeline_peer 300 RB_X=1 -- tools/timeline.py --cap 100000 --peer-optimizer --out $OUT/timeline_peer.json
+run timeline_nccl 150 RB_X=1 -- tools/timeline.py --cap 100000 --out $OUT/timeline_nccl.json
+run timeline_peer 150 RB_X=1 -- tools/timeline.py --cap 100000 --peer-optimizer --out $OUT/timeline_peer.json
 if [ "$N" = "8" ]; then
   run probe_nvls1 150 NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,NVLS,ENV NCCL_NVLS_ENABLE=1 -- tools/nccl_probe.py
   run probe_nvls0 150 NCCL_NVLS_ENABLE=0 -- tools/nccl_probe.py

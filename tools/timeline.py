@@ -111,9 +111,10 @@ def main():
         print(json.dumps({k: v for k, v in out.items() if k not in ("timeline", "by_kernel")}))
         for r in rows:
             print(f"{r['start_us']:8.1f} +{r['dur_us']:7.1f}  s{r['stream']:<3} {r['name'][:80]}")
+    sys.stdout.flush()
     if world > 1:
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+    os._exit(0)     # CUPTI + NCCL teardown has been seen to hang: everything is written, leave without it
 
 
 if __name__ == "__main__":
