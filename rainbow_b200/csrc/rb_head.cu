@@ -547,15 +547,34 @@ k_head_dh(const __grid_constant__ HeadDesc d, const float* __restrict__ dz, cons
   }
   const int m = tid >> 3, k = tid & 7;
   const float hv = (m < B) ? __ldg(h + (size_t)m * (2 * H) + s * H + k0 + k) : 0.0f;
+  // noise factors of this thread's weight chunks, requested while the copies are still in flight
+  constexpr int DH_MAXI = 8;
+  float4 ek_r = make_float4(0.f, 0.f, 0.f, 0.f);
+  float eo_r[DH_MAXI];
+  if (ei) {
+    ek_r = __ldg(reinterpret_cast<const float4*>(ei + k0 + (tid & 1) * 4));   // idx & 1 == tid & 1 (DH_T is even)
+#pragma unroll
+    for (int u = 0; u < DH_MAXI; ++u) {
+      const int idx = tid + u * DH_T;
+      eo_r[u] = (idx < Ns * 2) ? __ldg(eo + (idx >> 1)) : 0.0f;
+    }
+  }
   cp_async_wait_all();
   __syncthreads();
   if (ei) {  // W2 = mu + sigma * (eps_out[o] * eps_in[k]) in place
-    for (int idx = tid; idx < Ns * 2; idx += DH_T) {
+    for (int idx = tid, u = 0; idx < Ns * 2; idx += DH_T, ++u) {
       const int o = idx >> 1, c = (idx & 1) * 4;
       float4 w = *reinterpret_cast<const float4*>(Wm + o * DH_KB + c);
       const float4 sg = *reinterpret_cast<const float4*>(Wsg + o * DH_KB + c);
-      const float4 ek = __ldg(reinterpret_cast<const float4*>(ei + k0 + c));
-      const float e = __ldg(eo + o);
+      const float4 ek = ek_r;
+      float e = 0.0f;
+      if (u < DH_MAXI) {
+#pragma unroll
+        for (int q = 0; q < DH_MAXI; ++q)
+          if (q == u) e = eo_r[q];
+      } else {
+        e = __ldg(eo + o);
+      }
       w.x = fmaf(sg.x, e * ek.x, w.x); w.y = fmaf(sg.y, e * ek.y, w.y);
       w.z = fmaf(sg.z, e * ek.z, w.z); w.w = fmaf(sg.w, e * ek.w, w.w);
       *reinterpret_cast<float4*>(Wm + o * DH_KB + c) = w;
@@ -1150,7 +1169,7 @@ int rb_bias_grad(const float* grad_out, int B, int C, int HW, float* out, rb_str
   return rbi::check_launch("rb_bias_grad");
 }
 
-static int conv_wgrad_band_rows(int OH) { return OH >= 16 ? (OH + 3) / 4 : OH; }   // 4 bands of output rows per sample
+static int conv_wgrad_band_rows(int OH) { return OH >= 16 ? (OH + 7) / 8 : OH; }   // ~8 bands of output rows per sample
 
 int rb_conv_wgrad_scratch_elems(int B, int IC, int IH, int OC, int K, int stride) {
   if (B <= 0 || IC <= 0 || OC <= 0 || K <= 0 || stride <= 0 || IH < K) return 0;

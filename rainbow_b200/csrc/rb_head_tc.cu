@@ -358,14 +358,14 @@ k_head_reduce1(const float* __restrict__ part, int S, int M, int H, const float*
   const size_t slice = (size_t)M * ncols;
   const float4* src = reinterpret_cast<const float4*>(part + (size_t)m * ncols + c);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s0 = 0; s0 < S; s0 += 12) {
-    float4 pv[12];
+  for (int s0 = 0; s0 < S; s0 += 24) {             // every slice of the (usual) 17 in flight at once: one round trip
+    float4 pv[24];
 #pragma unroll
-    for (int u = 0; u < 12; ++u)
+    for (int u = 0; u < 24; ++u)
       pv[u] = (s0 + u < S) ? __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (size_t)(s0 + u) * slice))
                            : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int u = 0; u < 12; ++u) { acc.x += pv[u].x; acc.y += pv[u].y; acc.z += pv[u].z; acc.w += pv[u].w; }
+    for (int u = 0; u < 24; ++u) { acc.x += pv[u].x; acc.y += pv[u].y; acc.z += pv[u].z; acc.w += pv[u].w; }
   }
   const int st = c >= H ? 1 : 0, n = c - st * H;     // H % 4 == 0: a float4 never straddles the two streams
   const float* bmu = st ? bmu1 : bmu0;
