@@ -308,7 +308,8 @@ def ours(opts, cfg, rank, world, local):
     torch.cuda.set_device(dev)
     torch.manual_seed(shard_seed(0, rank))
     np.random.seed(123 + rank)
-    args = make_args(cfg, dev, peer_optimizer=opts.peer_optimizer)
+    peer = False if (world == 1 or opts.nccl or os.environ.get("RB_PEER", "1") == "0") else (True if opts.peer_optimizer else "auto")
+    args = make_args(cfg, dev, peer_optimizer=peer)
     cap, B = cfg["cap"], cfg["B"]
 
     # defer_appends: the e2e loop's 4 appends per update are written by ONE rb_append_batch launch that reads the frames in
@@ -489,7 +490,11 @@ def ours(opts, cfg, rank, world, local):
     line = {"metric": "learner updates/sec (batch32, 1M buffer, 51 atoms)", "value": value,
             "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_value / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(opts.config, cfg, world),
+            "config": dict(workload_config(opts.config, cfg, world),
+                           **({"gradient_exchange": ("peer-memory optimiser over NVLink: reduce-scatter by peer loads beside the conv backward, "
+                                                     "sharded clip+Adam, all-gather by " + ("NVSwitch multicast stores" if agent.optimiser.peer.multicast else "peer stores"))
+                               if agent.peer_optimizer else "NCCL all-reduce (head slice overlapped with the conv backward) + replicated clip+Adam"}
+                              if world > 1 else {})),
             "e2e": {"value": e2e_value, "unit": "updates/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": REPLAY_FREQUENCY * 84 * 84 * 4, "d2h_bytes_per_step": B * 4,
                     "what": f"per step: {REPLAY_FREQUENCY} x mem.append(host frame) -- staged in the replay's pinned ring and written by one rb_append_batch "
@@ -546,7 +551,9 @@ def main():
     ap.add_argument("--cpu-updates", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--peer-optimizer", action="store_true",
-                    help="N>1: fused reduce-scatter + clip + Adam + all-gather over NVLink peer memory instead of NCCL all-reduce")
+                    help="N>1: insist on the fused reduce-scatter + clip + Adam + all-gather over NVLink peer memory (the default tries "
+                         "it and falls back to NCCL all-reduce + replicated Adam if symmetric memory cannot be set up)")
+    ap.add_argument("--nccl", action="store_true", help="N>1: NCCL all-reduce + replicated Adam (no peer-memory optimiser)")
     ap.add_argument("--profile-steps", type=int, default=0, help="run this many steps inside cudaProfilerStart/Stop and exit")
     ap.add_argument("--profile-mode", default="graph", choices=["graph", "eager", "e2e"])
     opts = ap.parse_args()

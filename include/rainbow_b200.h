@@ -297,7 +297,9 @@ int rb_clip_adam(float* param, const float* grad, float* exp_avg, float* exp_avg
  * still runs); gred_part receives this rank's reduced part, multiplied by grad_scale (1/world for averaging).
  * rb_peer_adam_gather (after every segment's rb_peer_reduce, stream-ordered) publishes the partial norms, clips, runs Adam
  * on the owned parts -- gred / exp_avg / exp_avg_sq hold the parts of segment 0, then segment 1, back to back --, stores the
- * new parameters into every rank's buffer and returns when all ranks' parts have landed here.
+ * new parameters into every rank's buffer and returns when all ranks' parts have landed here.  multicast_param (optional,
+ * may be NULL): the NVLS multicast mapping of the parameter buffers (one address that the NVSwitch replicates to every
+ * rank); when given, the all-gather is a single multimem.st per 16 bytes instead of `world` peer stores.
  * rb_peer_clip_adam = rb_peer_reduce over [0, P) + rb_peer_adam_gather with that single segment.
  * Validated on 4 x B200 against NCCL all-reduce + rb_clip_adam (tools/peer_adam_check.py). */
 int rb_peer_scratch_bytes(void);
@@ -307,7 +309,7 @@ int rb_peer_reduce(const float* const* peer_grad, uint64_t* const* peer_flags, i
 int rb_peer_adam_gather(float* const* peer_param, uint64_t* const* peer_flags, double* const* peer_norms, int world, int rank,
                         int n_seg, const int64_t* seg_begin, const int64_t* seg_len, const float* gred, float* exp_avg,
                         float* exp_avg_sq, float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_count,
-                        uint64_t* epoch, void* scratch, float* norm_out, rb_stream_t stream);
+                        uint64_t* epoch, void* scratch, float* norm_out, float* multicast_param, rb_stream_t stream);
 int rb_peer_clip_adam(const float* const* peer_grad, float* const* peer_param, uint64_t* const* peer_flags,
                       double* const* peer_norms, int world, int rank, int64_t P, float* gred, float* exp_avg,
                       float* exp_avg_sq, float grad_scale, float max_norm, float lr, float beta1, float beta2, float eps,

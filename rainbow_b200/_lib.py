@@ -60,7 +60,7 @@ SIGNATURES = {
     "rb_peer_scratch_bytes": (C.c_int, []),
     "rb_peer_reduce": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i64, _i64, _f32, _vp, _vp, _vp, _vp]),
     "rb_peer_adam_gather": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32,
-                                      _vp, _vp, _vp, _vp, _vp]),
+                                      _vp, _vp, _vp, _vp, _vp, _vp]),
     "rb_peer_clip_adam": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _f32,
                                     _vp, _vp, _vp, _vp, _vp]),
     "rb_clip_adam_scratch_elems": (C.c_int, []),

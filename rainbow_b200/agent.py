@@ -180,9 +180,29 @@ class Agent:
         self.online_net.noise_seed = (self.online_net.noise_seed * 2 + 1 + 7919 * self.sync.rank) & (2 ** 63 - 1)
         self.target_net.noise_seed = (self.target_net.noise_seed * 2 + 2 + 7919 * self.sync.rank) & (2 ** 63 - 1)
 
-        self.peer_optimizer = bool(getattr(args, "peer_optimizer", False)) and self.sync.enabled
-        self.optimiser = FusedClipAdam(self.online_net, lr=args.learning_rate, eps=args.adam_eps, max_norm=self.norm_clip,
-                                       peer=self.peer_optimizer)
+        # peer_optimizer: "auto" (bench.py's multi-GPU default) tries the fused NVLink optimiser (csrc/rb_peer.cu) and falls
+        # back to NCCL all-reduce + replicated Adam on EVERY rank if any rank could not set up the symmetric memory;
+        # True insists (raises), False / absent keeps the NCCL path
+        want = getattr(args, "peer_optimizer", False)
+        self.peer_optimizer = bool(want) and self.sync.enabled
+        self.optimiser = None
+        if self.peer_optimizer:
+            err = None
+            try:
+                self.optimiser = FusedClipAdam(self.online_net, lr=args.learning_rate, eps=args.adam_eps, max_norm=self.norm_clip,
+                                               peer=True)
+            except Exception as e:   # noqa: BLE001 -- whatever went wrong, all ranks must take the same path
+                err = e
+            ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=self.device)
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                if want != "auto":
+                    raise _lib.RainbowB200Error(f"peer optimiser could not be set up on some rank (this rank: {err})")
+                warnings.warn(f"rainbow_b200: peer-memory optimiser unavailable ({err}); using NCCL all-reduce + replicated Adam")
+                self.peer_optimizer, self.optimiser = False, None
+        if self.optimiser is None:
+            self.optimiser = FusedClipAdam(self.online_net, lr=args.learning_rate, eps=args.adam_eps, max_norm=self.norm_clip,
+                                           peer=False)
         self.sync.broadcast_(self.optimiser.flat_param)  # identical initial parameters on every rank
         if self.peer_optimizer:
             self.sync.exchange = False   # the optimiser step does the gradient exchange itself

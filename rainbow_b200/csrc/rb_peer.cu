@@ -112,11 +112,18 @@ k_peer_reduce(const __grid_constant__ PeerBufs pb, const uint64_t* __restrict__ 
 
 // Phase 2: publish this rank's partial norm, global norm -> clip -> Adam on the owned parts -> parameter parts stored
 // into every rank's buffer.
+// one 16-byte store that the NVSwitch replicates into every rank's copy of the buffer (NVLS multicast mapping)
+__device__ __forceinline__ void multimem_st4(float* mc_addr, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(PEER_THREADS)
 k_peer_adam(const __grid_constant__ PeerBufs pb, const __grid_constant__ Segs sg, uint64_t* __restrict__ epoch_ptr,
             const float* __restrict__ gred, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
             const double* __restrict__ seg_norm, float max_norm, float lr, float b1, float b2, float eps,
-            int64_t* __restrict__ step_count, float* __restrict__ norm_out, unsigned int* __restrict__ ticket) {
+            int64_t* __restrict__ step_count, float* __restrict__ norm_out, unsigned int* __restrict__ ticket,
+            float* __restrict__ mc_param) {
   const uint64_t epoch = *epoch_ptr + 1;
   const int W = pb.world, r = pb.rank;
   if (blockIdx.x == 0 && threadIdx.x < W) {   // this rank's share of the squared norm, to every rank
@@ -155,9 +162,13 @@ k_peer_adam(const __grid_constant__ PeerBufs pb, const __grid_constant__ Segs sg
       }
       reinterpret_cast<float4*>(exp_avg + shard_off)[i] = m;
       reinterpret_cast<float4*>(exp_avg_sq + shard_off)[i] = v;
+      if (mc_param) {   // all-gather in the switch: ONE multicast store lands in every rank's parameter buffer
+        multimem_st4(mc_param + base + 4 * i, p);
+      } else {
 #pragma unroll
-      for (int q = 0; q < RB_MAX_PEERS; ++q)   // all-gather by peer stores
-        if (q < W) reinterpret_cast<float4*>(pb.param[q] + base)[i] = p;
+        for (int q = 0; q < RB_MAX_PEERS; ++q)   // all-gather by peer stores
+          if (q < W) reinterpret_cast<float4*>(pb.param[q] + base)[i] = p;
+      }
     }
     shard_off += part;
   }
@@ -202,12 +213,13 @@ int ctas_for(int64_t part) {
   int64_t want = (part / 4 + PEER_THREADS - 1) / PEER_THREADS;
   return (int)(want < 1 ? 1 : (want > PEER_MAX_CTAS ? PEER_MAX_CTAS : want));
 }
-// The reduce-scatter runs BESIDE the conv backward (whose library kernels need free SM slots to start): one CTA per SM is
-// enough to keep NVLink busy (eight 16-byte peer loads in flight per thread) and leaves room for them (a 592-CTA launch
-// filled every register file and delayed the concurrent dgrad by 30 us at N = 2, mgpu_2 timeline).
+// The reduce-scatter runs BESIDE the conv backward, whose library kernels (dgrad_engine: 512-thread CTAs that take a whole
+// SM's register file) cannot start on an SM that holds even one of our CTAs: with 148 CTAs the dgrad chain waited for the
+// reduce to finish (mgpu_8 timeline: dgrad at 228 us instead of 189 us).  32 CTAs x 256 threads x W 16-byte peer loads in
+// flight (~1 MB at W = 8) keep NVLink busy and leave 116 SMs to the backward.
 int reduce_ctas_for(int64_t part) {
   const int c = ctas_for(part);
-  return c > 148 ? 148 : c;
+  return c > 32 ? 32 : c;
 }
 
 // scratch layout: per segment PEER_MAX_CTAS doubles of CTA partials, then double seg_norm[PEER_SEGS], then tickets
@@ -241,7 +253,7 @@ int rb_peer_reduce(const float* const* peer_grad, uint64_t* const* peer_flags, i
 int rb_peer_adam_gather(float* const* peer_param, uint64_t* const* peer_flags, double* const* peer_norms, int world, int rank,
                         int n_seg, const int64_t* seg_begin, const int64_t* seg_len, const float* gred, float* exp_avg,
                         float* exp_avg_sq, float max_norm, float lr, float beta1, float beta2, float eps, int64_t* step_count,
-                        uint64_t* epoch, void* scratch, float* norm_out, rb_stream_t stream) {
+                        uint64_t* epoch, void* scratch, float* norm_out, float* multicast_param, rb_stream_t stream) {
   if (!peer_param || !peer_norms || !seg_begin || !seg_len || !gred || !exp_avg || !exp_avg_sq || !step_count || !epoch || !scratch)
     return rbi::fail(RB_ERR_INVAL, "rb_peer_adam_gather: null pointer");
   if (n_seg < 1 || n_seg > PEER_SEGS) return rbi::fail(RB_ERR_RANGE, "rb_peer_adam_gather: 1 or 2 segments");
@@ -261,7 +273,7 @@ int rb_peer_adam_gather(float* const* peer_param, uint64_t* const* peer_flags, d
   cudaStream_t st = (cudaStream_t)stream;
   k_peer_adam<<<ctas_for(biggest), PEER_THREADS, 0, st>>>(pb, sg, epoch, gred, exp_avg, exp_avg_sq, scratch_seg_norm(scratch), max_norm,
                                                         lr, beta1, beta2, eps, step_count, norm_out,
-                                                        scratch_tickets(scratch) + PEER_SEGS);
+                                                        scratch_tickets(scratch) + PEER_SEGS, multicast_param);
   rc = rbi::check_launch("rb_peer_adam_gather(adam)");
   if (rc != RB_OK) return rc;
   k_peer_fence<<<1, 32, 0, st>>>(pb, epoch);
@@ -277,7 +289,7 @@ int rb_peer_clip_adam(const float* const* peer_grad, float* const* peer_param, u
   if (rc != RB_OK) return rc;
   const int64_t b = 0, l = P;
   return rb_peer_adam_gather(peer_param, peer_flags, peer_norms, world, rank, 1, &b, &l, gred, exp_avg, exp_avg_sq, max_norm, lr,
-                             beta1, beta2, eps, step_count, epoch, scratch, norm_out, stream);
+                             beta1, beta2, eps, step_count, epoch, scratch, norm_out, nullptr, stream);
 }
 
 }  // extern "C"

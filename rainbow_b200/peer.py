@@ -32,7 +32,12 @@ def _peer_allocate(total_bytes, device, group):
     buf.zero_()
     handle = symm_mem.rendezvous(buf, grp.group_name)
     _KEEP.append(handle)
-    return buf, [int(p) for p in handle.buffer_ptrs]
+    mc = 0
+    try:   # NVLS multicast mapping of the same allocation (0 when the fabric / driver does not offer it)
+        mc = int(handle.multicast_ptr or 0)
+    except Exception:
+        mc = 0
+    return buf, [int(p) for p in handle.buffer_ptrs], mc
 
 
 class PeerOptimizerState:
@@ -64,7 +69,11 @@ class PeerOptimizerState:
         nbytes = self.world * 8
         self._off = (0, pbytes, 2 * pbytes, 2 * pbytes + 256 * (-(-fbytes // 256)))
         total = self._off[3] + 256 * (-(-nbytes // 256))
-        self.buf, bases = _peer_allocate(total, device, group)
+        self.buf, bases, mc = _peer_allocate(total, device, group)
+        import os
+        # the parameter all-gather goes through the NVSwitch multicast mapping when there is one (RB_PEER_MULTICAST=0: peer stores)
+        self.multicast = bool(mc) and os.environ.get("RB_PEER_MULTICAST", "1") != "0"
+        self._mc_param = C.c_void_p(mc + self._off[0]) if self.multicast else None
         self.flat_param = self.buf[self._off[0]:self._off[0] + pbytes].view(torch.float32)
         self.flat_grad = self.buf[self._off[1]:self._off[1] + pbytes].view(torch.float32)
         n = self.world
@@ -112,5 +121,5 @@ class PeerOptimizerState:
             self._peer_param, self._peer_flags, self._peer_norms, self.world, self.rank, len(self.segments), self._seg_begin,
             self._seg_len, _lib.ptr(self.gred), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), float(max_norm), float(lr),
             float(betas[0]), float(betas[1]), float(eps), _lib.ptr(self.step_count), _lib.ptr(self.epoch),
-            _lib.ptr(self._scratch), _lib.ptr(self.grad_norm), _lib.stream()))
+            _lib.ptr(self._scratch), _lib.ptr(self.grad_norm), self._mc_param, _lib.stream()))
         self._reduced = [False] * len(self.segments)

@@ -60,5 +60,5 @@ for it in range(6):
     assert torch.equal(chk, peer.flat_param), "ranks hold different parameters"
 dist.barrier()
 if rank == 0:
-    print(f"peer optimiser OK (world {world}, segments {peer.segments})")
+    print(f"peer optimiser OK (world {world}, segments {peer.segments}, multicast all-gather {peer.multicast})")
 dist.destroy_process_group()
