@@ -78,18 +78,30 @@ k_peer_reduce(const __grid_constant__ PeerBufs pb, const uint64_t* __restrict__ 
   const int64_t base = seg_begin + (int64_t)r * part;
   double acc = 0.0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (part >> 2); i += stride) {
-    float4 g[RB_MAX_PEERS];
+  const int64_t n4 = part >> 2;
+  constexpr int UN = 4;   // grid-stride iterations whose peer loads are all issued before any is consumed (few CTAs, deep queues)
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * UN) {
+    float4 g[UN][RB_MAX_PEERS];
 #pragma unroll
-    for (int p = 0; p < RB_MAX_PEERS; ++p)   // all peer loads of this element in flight together
-      if (p < W) g[p] = *reinterpret_cast<const float4*>(pb.grad[p] + base + 4 * i);
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < UN; ++u) {
+      const int64_t i = i0 + u * stride;
 #pragma unroll
-    for (int p = 0; p < RB_MAX_PEERS; ++p)   // fixed rank order: deterministic
-      if (p < W) { s.x += g[p].x; s.y += g[p].y; s.z += g[p].z; s.w += g[p].w; }
-    s.x *= grad_scale; s.y *= grad_scale; s.z *= grad_scale; s.w *= grad_scale;
-    reinterpret_cast<float4*>(gred)[i] = s;
-    acc += (double)s.x * s.x + (double)s.y * s.y + (double)s.z * s.z + (double)s.w * s.w;
+      for (int p = 0; p < RB_MAX_PEERS; ++p)
+        if (p < W && i < n4) g[u][p] = *reinterpret_cast<const float4*>(pb.grad[p] + base + 4 * i);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n4) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < RB_MAX_PEERS; ++p)   // fixed rank order: deterministic
+          if (p < W) { s.x += g[u][p].x; s.y += g[u][p].y; s.z += g[u][p].z; s.w += g[u][p].w; }
+        s.x *= grad_scale; s.y *= grad_scale; s.z *= grad_scale; s.w *= grad_scale;
+        reinterpret_cast<float4*>(gred)[i] = s;
+        acc += (double)s.x * s.x + (double)s.y * s.y + (double)s.z * s.z + (double)s.w * s.w;
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -215,11 +227,12 @@ int ctas_for(int64_t part) {
 }
 // The reduce-scatter runs BESIDE the conv backward, whose library kernels (dgrad_engine: 512-thread CTAs that take a whole
 // SM's register file) cannot start on an SM that holds even one of our CTAs: with 148 CTAs the dgrad chain waited for the
-// reduce to finish (mgpu_8 timeline: dgrad at 228 us instead of 189 us).  32 CTAs x 256 threads x W 16-byte peer loads in
-// flight (~1 MB at W = 8) keep NVLink busy and leave 116 SMs to the backward.
+// reduce to finish (mgpu_8 timeline: dgrad at 228 us instead of 189 us).  64 CTAs x 256 threads x 4 x W 16-byte peer loads
+// in flight (2 MB at W = 2) keep NVLink busy and leave 84 SMs to the backward (32 CTAs with one iteration in flight
+// took 213 us for the 13.6 MB of N = 2: mgpu_q2 timeline).
 int reduce_ctas_for(int64_t part) {
   const int c = ctas_for(part);
-  return c > 32 ? 32 : c;
+  return c > 64 ? 64 : c;
 }
 
 // scratch layout: per segment PEER_MAX_CTAS doubles of CTA partials, then double seg_norm[PEER_SEGS], then tickets

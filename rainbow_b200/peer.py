@@ -71,8 +71,10 @@ class PeerOptimizerState:
         total = self._off[3] + 256 * (-(-nbytes // 256))
         self.buf, bases, mc = _peer_allocate(total, device, group)
         import os
-        # the parameter all-gather goes through the NVSwitch multicast mapping when there is one (RB_PEER_MULTICAST=0: peer stores)
-        self.multicast = bool(mc) and os.environ.get("RB_PEER_MULTICAST", "1") != "0"
+        # RB_PEER_MULTICAST=1: the parameter all-gather goes through the NVSwitch multicast mapping (one multimem.st per 16
+        # bytes instead of `world` peer stores).  Validated (tools/peer_adam_check.py) but not faster at N = 2 (mgpu_q2:
+        # k_peer_adam 70 us vs 44 us with peer stores), so it is opt-in until it has been measured at N = 8.
+        self.multicast = bool(mc) and os.environ.get("RB_PEER_MULTICAST", "0") == "1"
         self._mc_param = C.c_void_p(mc + self._off[0]) if self.multicast else None
         self.flat_param = self.buf[self._off[0]:self._off[0] + pbytes].view(torch.float32)
         self.flat_grad = self.buf[self._off[1]:self._off[1] + pbytes].view(torch.float32)
