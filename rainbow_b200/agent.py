@@ -457,8 +457,9 @@ class Agent:
                             self.sync.all_reduce_(self.optimiser.flat_grad[self.optimiser.conv_end:])
                         head_reduced = torch.cuda.Event()
                         head_reduced.record(s_tg)
-                grads_done = on.conv_backward_into_grads(acts, dx.view_as(acts[-1]), s_ns,
-                                                         first_layer_stream=None if self.sync.enabled else s_tg)
+                # (a separate stream for the first layer's own weight-gradient kernel was tried and lost: it then overlaps
+                # cuDNN's wgrad of the layer above and both slow down -- r02e vs r02f timelines)
+                grads_done = on.conv_backward_into_grads(acts, dx.view_as(acts[-1]), s_ns)
                 main.wait_event(grads_done)
                 if self.sync.enabled:
                     self.sync.all_reduce_(self.optimiser.flat_grad[:self.optimiser.conv_end])
