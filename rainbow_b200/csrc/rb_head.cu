@@ -654,7 +654,7 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
   extern __shared__ __align__(16) float b1_ring[];     // [B1_STAGES][B1_STAGE]
   __shared__ __align__(16) float Xs[32][B1_K + 8];    // x slice [m][k]  (B operand of the weight-gradient product)
   __shared__ __align__(16) float Red[32][B1_K + 4];   // dx partial handed over the cluster
-  __shared__ float Eo[B1_STAGES][B1_O];               // eps_out of the staged chunks' rows
+  __shared__ float EoAll[512];                         // eps_out of every row this CTA walks (H / 2 <= 512), fetched once
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x;
   // warps 0-3: weight-gradient tile [32 o][32 k] of the current chunk; warps 4-7: input gradient [32 m][32 k].  Warp w of a
@@ -681,10 +681,12 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
       const bool row_ok = st_r < B;
       cp_async16_zfill(Dm(st) + st_r * B1_LDD + st_c, row_ok ? dh + (size_t)st_r * (2 * H) + s * H + ob + st_c : dh, row_ok);
       cp_async16_zfill(Dt(st) + st_r * B1_LDD + st_c, dhT + (size_t)(s * H + ob + st_r) * 32 + st_c, true);
-      if (st_c == 0) Eo[st][st_r] = eo ? __ldg(eo + ob + st_r) : 0.0f;
     }
     cp_async_commit();
   };
+  // (a per-chunk __ldg of eps_out inside issue() put one exposed global latency in front of every chunk: r02 ncu, 12 % of
+  // the kernel's stall samples on the dependent STS)
+  for (int i = tid; i < H / 2; i += B1_T) EoAll[i] = eo ? __ldg(eo + o_begin + i) : 0.0f;
 
 #pragma unroll
   for (int c = 0; c < B1_STAGES - 1; ++c) issue(c);
@@ -722,7 +724,7 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
     if (ei) {                         // W = mu + sigma * (eps_out[o] * eps_in[k]) in place   (model.py:39,43)
       float4 w = *reinterpret_cast<const float4*>(Wm(st) + st_r * B1_LDW + st_c);
       const float4 sg4 = *reinterpret_cast<const float4*>(Wsg(st) + st_r * B1_LDW + st_c);
-      const float e = Eo[st][st_r];
+      const float e = EoAll[c * B1_O + st_r];
       w.x = fmaf(sg4.x, e * e4s.x, w.x); w.y = fmaf(sg4.y, e * e4s.y, w.y);
       w.z = fmaf(sg4.z, e * e4s.z, w.z); w.w = fmaf(sg4.w, e * e4s.w, w.w);
       *reinterpret_cast<float4*>(Wm(st) + st_r * B1_LDW + st_c) = w;
@@ -742,7 +744,7 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
           const size_t off = (size_t)(ob + ol) * K + k0 + n0 + 2 * tig;
           const float g0 = ga[2 * hrow], g1 = ga[2 * hrow + 1];
           __stcs(reinterpret_cast<float2*>(g.w1_mu[s] + off), make_float2(g0, g1));
-          const float e = Eo[st][ol];
+          const float e = EoAll[c * B1_O + ol];
           __stcs(reinterpret_cast<float2*>(g.w1_sig[s] + off), make_float2(g0 * (e * ei0), g1 * (e * ei1v)));
         }
       }
@@ -751,7 +753,7 @@ k_head_bwd1(const __grid_constant__ HeadDesc d, const __grid_constant__ HeadGrad
         float bs = 0.0f;
         for (int m = 0; m < 32; ++m) bs += Ds[m * B1_LDD + rt];
         g.b1_mu[s][ob + rt] = bs;
-        g.b1_sig[s][ob + rt] = bs * Eo[st][rt];
+        g.b1_sig[s][ob + rt] = bs * EoAll[c * B1_O + rt];
       }
     } else {
       // ---- input gradient [32 m][32 k] += dh chunk [m][o] x composed W chunk [o][k]: reduction over the chunk's rows ----
@@ -1150,6 +1152,7 @@ int rb_head_backward(const rb_head_params* p, const rb_head_grads* gr, const flo
   rc = rbi::check_launch("rb_head_backward(dh)");
   if (rc != RB_OK) return rc;
   if (parts & RB_HEAD_BWD_LAYER1) {
+    if (d.H > 1024) return rbi::fail(RB_ERR_RANGE, "rb_head_backward: hidden <= 1024 required");
     dim3 grid(d.K1 / B1_K, 4);
     rbi::ProfScope prof_(RB_K_HEAD_BWD1, st);
     const size_t smem_b1 = (size_t)B1_STAGES * B1_STAGE * sizeof(float);
