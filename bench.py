@@ -222,7 +222,7 @@ def cpu_arm(cfg, updates, warmup, budget_s, also_gpu=None):
         ups, dt, threads, done, extra = r
         return ups, dt, threads, done, "reference", (
             f"{done} updates of the same workload (each preceded by {REPLAY_FREQUENCY} appends) after {warmup} warm-up updates, {dt:.1f} s; "
-            f"UNMODIFIED reference modules (oracle/_ref: memory.py, agent.py, model.py, sha256-checked copies) on torch-CPU with "
+            f"UNMODIFIED reference modules (oracle/_ref/reference_modules.zip: memory.py, agent.py, model.py, sha256-checked) on torch-CPU with "
             f"{threads} threads; the 1M-record replay object is assembled without the reference's 242 s list constructor"), extra
     ups, dt, threads, done = run_cpu_port(cfg, updates, warmup, with_appends=True, budget_s=budget_s)
     return ups, dt, threads, done, "port", (

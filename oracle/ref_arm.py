@@ -1,7 +1,8 @@
 """The UNMODIFIED reference as a bench arm -- TEST / BASELINE INFRASTRUCTURE ONLY (bench.py's cpu legs import this).
 
-`make -C oracle _ref` copies the reference's three hot-path modules (memory.py, agent.py, model.py) byte for byte into
-oracle/_ref/ (hash-checked, git-ignored).  This module imports them from there under the reference's own module names,
+`make -C oracle _ref` packs the reference's three hot-path modules (memory.py, agent.py, model.py), hash-checked and byte
+for byte, into oracle/_ref/reference_modules.zip (git-ignored build output).  This module imports them from the archive
+(zipimport) under the reference's own module names,
 builds the BASELINE.md synthetic replay WITHOUT the reference's 242-second Python-list constructor (memory.py:19: the
 SegmentTree object is assembled field by field, `data` as np.zeros(cap, Transition_dtype); every METHOD that runs
 afterwards is the reference's own) and times `dqn.reset_noise(); dqn.learn(mem)` (main.py:150-151) on a device of choice.
@@ -16,12 +17,12 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF_DIR = os.path.join(HERE, "_ref")
+REF_DIR = os.path.join(HERE, "_ref", "reference_modules.zip")
 _mods = None
 
 
 def available():
-    return all(os.path.isfile(os.path.join(REF_DIR, f)) for f in ("memory.py", "agent.py", "model.py"))
+    return os.path.isfile(REF_DIR)
 
 
 def modules():
@@ -33,7 +34,7 @@ def modules():
         sys.path.insert(0, REF_DIR)
         try:
             m = tuple(importlib.import_module(k) for k in ("memory", "agent", "model"))
-            assert all(os.path.dirname(os.path.abspath(x.__file__)) == REF_DIR for x in m)
+            assert all(os.path.abspath(x.__file__).startswith(REF_DIR) for x in m)
         finally:
             sys.path.remove(REF_DIR)
             for k, v in saved.items():
