@@ -436,6 +436,31 @@ def ours(opts, cfg, rank, world, local):
     agent.use_cuda_graph = True
     log("kernel timing pass done")
 
+    # ---- context only (N = 1): the same update with the documented TF32 switch for the conv body (north star: "tensor
+    # cores only there").  Not the headline: the parity tests and `value` run the fp32 policy the Agent sets by default.
+    tf32_ctx = None
+    if world == 1 and not opts.no_cpu_baseline:
+        import argparse as _ap
+        a2 = Agent(_ap.Namespace(**{**vars(args), "tf32": True}), FakeEnv())     # sets the process-wide TF32 flags
+        try:
+            for _ in range(Agent.GRAPH_WARMUP + 4):
+                a2.reset_noise()
+                a2.learn(mem)
+
+            def step_tf32(i):
+                a2.reset_noise()
+                a2.learn(mem)
+
+            ms_tf32 = timed(step_tf32, 100)
+            tf32_ctx = {"ms_per_step": ms_tf32 / 100, "value": 100 / (ms_tf32 * 1e-3), "unit": "updates/s",
+                        "what": "Agent(args.tf32=True): cuDNN may use TF32 tensor-core kernels for the conv body (heads unchanged); outside "
+                                "the 1e-5 parity bar, reported for context only"}
+        finally:
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            del a2
+        log(f"tf32 conv context: {tf32_ctx['ms_per_step']:.3f} ms/step")
+
     if rank != 0:
         return
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -505,6 +530,8 @@ def ours(opts, cfg, rank, world, local):
             # k_sqnorm, k_clip_adam, k_tree_update_warp = 18 (the remaining ~19 graph nodes per step are cuDNN / ATen)
             "gpu_launches": int(round(K * sum(launches_per_step.values()))),
             "clocks": clocks, "roofline": roofline}
+    if tf32_ctx is not None:
+        line["tf32_conv_context"] = tf32_ctx
     if world == 1 and not opts.no_cpu_baseline:
         del agent, mem, tr                                  # give the 7 GB of HBM back before the reference's GPU leg
         torch.cuda.empty_cache()
