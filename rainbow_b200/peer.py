@@ -26,6 +26,11 @@ _KEEP = []   # symmetric-memory handles must outlive every kernel that uses the 
 def _peer_allocate(total_bytes, device, group):
     """A zeroed `total_bytes` uint8 buffer on `device` that every rank of `group` can address (torch symmetric memory:
     cuMem allocation + handle exchange): returns (local tensor, [base pointer of every rank's buffer as seen from here])."""
+    import os
+    if os.environ.get("RB_PEER_MULTICAST", "0") != "1":
+        # the NVSwitch multicast mapping is not used by default, so torch is told not to create one: multicast-group creation
+        # goes through the fabric manager, the step the round-1 communicator hang sat in (DESIGN.md 6)
+        os.environ.setdefault("TORCH_SYMM_MEM_DISABLE_MULTICAST", "1")
     import torch.distributed._symmetric_memory as symm_mem
     grp = group if group is not None else dist.group.WORLD
     buf = symm_mem.empty(total_bytes, dtype=torch.uint8, device=device)
