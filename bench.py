@@ -283,14 +283,25 @@ def algorithmic_bytes(cfg, P, noisy_elems):
     }
 
 
-def csrc_sha256():
+def csrc_sha256(files=None):
+    """sha256 over rainbow_b200/csrc/ (all .cu / .cuh, or the given file names, in sorted order)."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "rainbow_b200", "csrc")
-    for fn in sorted(os.listdir(d)):
+    for fn in sorted(os.listdir(d) if files is None else files):
         if fn.endswith((".cu", ".cuh")):
             h.update(open(os.path.join(d, fn), "rb").read())
     return h.hexdigest()
+
+
+# which translation unit (+ the shared header) a kernel's DRAM-traffic capture depends on
+KERNEL_SOURCES = {"head_fc1": ["rb_head_tc.cu"], "head_reduce1": ["rb_head_tc.cu"], "head_fc2": ["rb_head.cu"], "head_dh": ["rb_head.cu"],
+                  "head_bwd1": ["rb_head.cu"], "head_wgrad2": ["rb_head.cu"], "bias_grad": ["rb_head.cu"], "conv_wgrad": ["rb_head.cu"],
+                  "noise_factors": ["rb_head.cu"]}
+
+
+def kernel_source_sha(name):
+    return csrc_sha256(sorted(KERNEL_SOURCES.get(name, ["rb_kernels.cu"]) + ["rb_internal.cuh"]))
 
 
 def ours(opts, cfg, rank, world, local):
@@ -493,11 +504,12 @@ def ours(opts, cfg, rank, world, local):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if tj.get("csrc_sha256") == csrc_sha256():
+        # the capture is quoted only while the translation unit that holds the kernel is byte-identical to the captured one
+        if tj.get("source_sha256", {}).get(dominant) == kernel_source_sha(dominant):
             traffic = tj.get(opts.config, {}).get(dominant)
             traffic_note = f"dram__bytes_read.sum + dram__bytes_write.sum per launch, {tj.get('source', 'profiles/')}"
         else:
-            traffic_note = "profiles/traffic.json was captured from other kernel sources (csrc sha256 differs): not quoted"
+            traffic_note = "profiles/traffic.json was captured from other sources of this kernel (sha256 differs): not quoted"
     roofline = {"kernel": "k_" + dominant, "bound": "hbm", "achieved": d["GBps"], "peak": peak, "unit": "GB/s", "frac": d["frac"],
                 "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": d["bytes"], "us_per_launch": d["us"],

@@ -10,8 +10,9 @@ Per update (csrc/rb_peer.cu)
 cross-GPU ordering is epoch flags in the same symmetric allocation, never the host.  Replaces
 `all_reduce(flat_grad); rb_clip_adam` (replicated 192 MB optimiser pass on every rank).
 
-Validated on 4 x B200 against the NCCL path (tools/peer_adam_check.py: max |dp| 1.5e-8 over 6 steps, ranks bit-identical).
-Opt-in: `args.peer_optimizer = True` (Agent) / `bench.py --peer-optimizer`.
+Validated on 2, 4 and 8 x B200 against the NCCL path (tools/peer_adam_check.py: max |dp| 1.5e-8 over 6 steps, ranks
+bit-identical).  `args.peer_optimizer`: True | "auto" (falls back to the NCCL all-reduce when symmetric memory cannot be set
+up; bench.py's default for world > 1) | False.
 """
 import ctypes as C
 
