@@ -247,12 +247,20 @@ def reference_arm(opts, cfg, rank):
     emit(line)
 
 
-def workload_config(name, cfg, gpus):
+def workload_config(name, cfg, gpus, param_elems=None):
+    if param_elems is None:
+        l2 = "host arm: no GPU cache involved"
+    else:
+        # distinct device addresses one update walks: online + target parameters, the gradient, both Adam moments, the [s; s'] batch
+        mb = (5 * param_elems * 4 + 2 * cfg["B"] * 4 * 84 * 84 * 4) / 1e6
+        l2 = (f"no explicit flush: an update walks {mb:.0f} MB of distinct addresses (two parameter sets, gradient, two Adam moments, "
+              f"the state batch) -- {'more' if mb > 126 else 'LESS'} than the 126 MB L2"
+              f"{'' if mb > 126 else ' (this configuration stays L2-resident, in training as here)'} -- plus {2 * cfg['B']} random "
+              f"4-frame states of a {cfg['cap'] * 7056 / 1e9:.1f} GB frame ring")
     return {"workload": f"{name}: synthetic 84x84x4 transitions, {cfg['cap']}-transition replay per GPU, batch {cfg['B']} per GPU, "
                         f"51 atoms, n={cfg['n']}, {cfg['arch']} net hidden {cfg['hidden']}, {ACTIONS} actions",
             "global_batch": cfg["B"] * gpus, "parallelism": f"dp{gpus} (independent replay per rank, grad all-reduce)" if gpus > 1 else "single",
-            "l2": "no explicit flush: a step touches ~0.5 GB (parameters, Adam state, noise, activations) of distinct "
-                  "addresses plus random frames of a 7 GB ring, against a 126 MB L2"}
+            "l2": l2}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -527,7 +535,7 @@ def ours(opts, cfg, rank, world, local):
     line = {"metric": "learner updates/sec (batch32, 1M buffer, 51 atoms)", "value": value,
             "unit": "updates/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_value / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(opts.config, cfg, world),
+            "config": dict(workload_config(opts.config, cfg, world, P),
                            **({"gradient_exchange": ("peer-memory optimiser over NVLink: reduce-scatter by peer loads beside the conv backward, "
                                                      "sharded clip+Adam, all-gather by " + ("NVSwitch multicast stores" if agent.optimiser.peer.multicast else "peer stores"))
                                if agent.peer_optimizer else "NCCL all-reduce (head slice overlapped with the conv backward) + replicated clip+Adam"}
