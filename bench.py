@@ -545,9 +545,10 @@ def ours(opts, cfg, rank, world, local):
                     "what": f"per step: {REPLAY_FREQUENCY} x mem.append(host frame) -- staged in the replay's pinned ring and written by one rb_append_batch "
                             "launch that reads them in place over PCIe -- + dqn.reset_noise() + dqn.learn(mem) + per-sample loss copied to pinned host "
                             "memory and read by the host one step behind the GPU (double buffer)"},
-            # our kernels launched in the timed `value` region, per step: 2 k_noise_factors, k_tree_sample, k_gather,
-            # 2 x (k_head_fc<.,1> + k_head_fc<.,2>), k_c51_dueling, k_head_wgrad2, k_head_dh, k_head_bwd1, 3 k_bias_grad,
-            # k_sqnorm, k_clip_adam, k_tree_update_warp = 18 (the remaining ~19 graph nodes per step are cuDNN / ATen)
+            # our kernels launched in the timed `value` region, counted per kernel id during the eager replay of the same step
+            # (C2: 2 k_noise_factors, k_tree_sample, k_gather, 2 x (k_head_fc1_tc + k_head_reduce1 + k_head_fc2), k_c51_dueling,
+            # k_head_wgrad2, k_head_dh, k_head_bwd1, 2 k_bias_grad, rb_conv_wgrad (two kernels under one id), k_sqnorm, k_clip_adam,
+            # k_tree_update_warp = 20 ids per step; the other graph nodes are cuDNN / ATen)
             "gpu_launches": int(round(K * sum(launches_per_step.values()))),
             "clocks": clocks, "roofline": roofline}
     if tf32_ctx is not None:
