@@ -53,6 +53,25 @@ def test_abi_argument_validation_without_gpu():
     assert lib.rb_clip_adam(one, one, one, one, 0, 1.0, 10.0, 1e-4, 0.9, 0.999, 1e-4, one, one, None, None, None) == -22
     tot, n = C.c_double(), C.c_int()
     assert lib.rb_profile_collect(99, C.byref(tot), C.byref(n)) == -22
+    # entry points added with ABI version 2
+    assert lib.rb_q_values(one, 4, 6, 51, one, None, None, None, None) == -22                       # no output requested
+    assert lib.rb_q_values(one, 4, 6, 200, one, one, None, None, None) == -34                       # atoms > RB_MAX_ATOMS
+    assert lib.rb_conv_wgrad(one, one, 32, 4, 84, 84, 32, 7, 4, one, one, None, None) == -34        # kernel size not instantiated
+    assert lib.rb_conv_wgrad(one, one, 32, 32, 20, 20, 64, 4, 2, one, one, None, None) == -34       # needs more than 256 threads
+    assert lib.rb_conv_wgrad(one, None, 32, 4, 84, 84, 32, 8, 4, one, one, None, None) == -22
+    assert lib.rb_conv_wgrad_scratch_elems(32, 4, 84, 32, 8, 4) == 32 * 7 * (32 * 4 * 8 * 8 + 32)   # 20 output rows in 7 bands of 3
+    assert lib.rb_conv_wgrad_scratch_elems(32, 4, 4, 32, 8, 4) == 0
+    two = (C.c_void_p * 2)(8, 8)
+    assert lib.rb_peer_reduce(two, two, 2, 0, 2, 0, 64, 0.5, one, one, one, None) == -34            # segment id
+    assert lib.rb_peer_reduce(two, two, 2, 0, 0, 0, 60, 0.5, one, one, one, None) == -22            # not a multiple of 4 * world
+    assert lib.rb_peer_reduce(two, two, 2, 2, 0, 0, 64, 0.5, one, one, one, None) == -34            # rank >= world
+    assert lib.rb_peer_reduce(two, two, 9, 0, 0, 0, 144, 0.5, one, one, one, None) == -34           # world > RB_MAX_PEERS
+    beg, ln = (C.c_int64 * 2)(0, 64), (C.c_int64 * 2)(64, 60)
+    assert lib.rb_peer_adam_gather(two, two, two, 2, 0, 3, beg, ln, one, one, one, 10.0, 1e-4, 0.9, 0.999, 1e-4, one, one, one,
+                                   None, None, None) == -34                                        # at most two segments
+    assert lib.rb_peer_adam_gather(two, two, two, 2, 0, 2, beg, ln, one, one, one, 10.0, 1e-4, 0.9, 0.999, 1e-4, one, one, one,
+                                   None, None, None) == -22                                        # second segment: 60 elements
+    assert lib.rb_peer_scratch_bytes() >= (2 * 592 + 2) * 8
 
 
 def test_no_cpu_fallback():
@@ -329,3 +348,19 @@ def test_oracle_clip_adam_follows_the_reference_trajectory():
         worst = max(worst, float(np.abs(p - want).max()))
         p[:] = want                   # follow the reference exactly from here on (m, v stay the oracle's)
     assert worst <= 4e-9, worst
+
+
+def test_bench_traffic_capture_is_keyed_by_kernel_source():
+    """profiles/traffic.json carries, per kernel, the hash of the source file the capture was taken from; bench.py quotes a
+    capture only while that file is unchanged (a stale capture must never be quoted)."""
+    import json
+    sys.path.insert(0, ROOT)
+    import bench
+    tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    assert set(tj["source_sha256"]) == set(tj["C2"])
+    for name in tj["C2"]:
+        assert len(bench.kernel_source_sha(name)) == 64
+    # a kernel of rb_head.cu does not depend on rb_kernels.cu and the other way round
+    assert bench.KERNEL_SOURCES["head_bwd1"] == ["rb_head.cu"] and "clip_adam" not in bench.KERNEL_SOURCES
+    assert bench.kernel_source_sha("clip_adam") == bench.csrc_sha256(["rb_internal.cuh", "rb_kernels.cu"])
+    assert bench.kernel_source_sha("clip_adam") != bench.kernel_source_sha("head_bwd1")
